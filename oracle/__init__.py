@@ -1,0 +1,6 @@
+"""CPU oracle for the hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  PARITY UNPINNED against the upstream binary:
+see the header of ``oracle/oracle.cpp`` and DESIGN.md.
+"""
