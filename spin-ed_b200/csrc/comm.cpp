@@ -1,0 +1,143 @@
+// comm.cpp -- one process per GPU; collectives are NCCL over NVLink/NVSwitch.
+//
+// The reference is a single shared-memory process (OpenMP inside liblattice_symmetries,
+// /root/reference/configure:63); sharding rows over GPUs is new.  NCCL is bound at run time with
+// dlopen so that libsped.so itself loads on a machine without NCCL (symbol-export tests) and so
+// that, inside a PyTorch process, the NCCL already mapped by torch is the one used.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "internal.h"
+
+namespace sped {
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi& api() {
+  static NcclApi a;
+  if (a.handle) return a;
+  char const* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (char const* n : names) {
+    a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.handle) break;
+  }
+  if (!a.handle) fail(SPED_NCCL_ERROR, std::string("cannot load NCCL: ") + dlerror());
+  auto load = [&](char const* sym) {
+    void* p = dlsym(a.handle, sym);
+    if (!p) fail(SPED_NCCL_ERROR, std::string("NCCL symbol missing: ") + sym);
+    return p;
+  };
+  a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(load("ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(load("ncclCommInitRank"));
+  a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(load("ncclCommDestroy"));
+  a.AllGather = reinterpret_cast<decltype(a.AllGather)>(load("ncclAllGather"));
+  a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(load("ncclAllReduce"));
+  a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(load("ncclBroadcast"));
+  a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(load("ncclGroupStart"));
+  a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(load("ncclGroupEnd"));
+  a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(load("ncclGetErrorString"));
+  return a;
+}
+
+void nccl_check(ncclResult_t r, char const* what) {
+  if (r != ncclSuccess) fail(SPED_NCCL_ERROR, std::string(what) + ": " + api().GetErrorString(r));
+}
+
+Comm g_comm;
+
+}  // namespace
+
+Comm& comm() { return g_comm; }
+
+static_assert(sizeof(ncclUniqueId) == 128, "unique id is exchanged as 128 bytes");
+
+void comm_unique_id(void* out128) {
+  ncclUniqueId id;
+  nccl_check(api().GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out128, &id, 128);
+}
+
+void comm_init(int world, int rank, void const* id128) {
+  if (world < 1 || rank < 0 || rank >= world) fail(LS_INVALID_ARGUMENT, "invalid world size / rank");
+  if (g_comm.nccl) fail(LS_INVALID_ARGUMENT, "communicator already initialised");
+  g_comm.world = world;
+  g_comm.rank = rank;
+  if (world == 1) return;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclComm_t c;
+  nccl_check(api().CommInitRank(&c, world, id, rank), "ncclCommInitRank");
+  g_comm.nccl = c;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_comm.stream, cudaStreamNonBlocking));
+}
+
+void comm_finalize() {
+  if (g_comm.nccl) {
+    api().CommDestroy(static_cast<ncclComm_t>(g_comm.nccl));
+    g_comm.nccl = nullptr;
+  }
+  if (g_comm.stream) {
+    cudaStreamDestroy(g_comm.stream);
+    g_comm.stream = nullptr;
+  }
+  g_comm.world = 1;
+  g_comm.rank = 0;
+}
+
+void comm_allgather_inplace(void* buf, size_t chunk_bytes, cudaStream_t s) {
+  if (!g_comm.active()) return;
+  char* base = static_cast<char*>(buf);
+  nccl_check(api().AllGather(base + (size_t)g_comm.rank * chunk_bytes, base, chunk_bytes, ncclChar,
+                             static_cast<ncclComm_t>(g_comm.nccl), s),
+             "ncclAllGather");
+}
+
+void comm_allreduce_sum_f64(double* dev, size_t count, cudaStream_t s) {
+  if (!g_comm.active() || count == 0) return;
+  nccl_check(api().AllReduce(dev, dev, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(g_comm.nccl), s),
+             "ncclAllReduce");
+}
+
+void comm_allreduce_sum_u64(unsigned long long* dev, size_t count, cudaStream_t s) {
+  if (!g_comm.active() || count == 0) return;
+  nccl_check(api().AllReduce(dev, dev, count, ncclUint64, ncclSum, static_cast<ncclComm_t>(g_comm.nccl), s),
+             "ncclAllReduce");
+}
+
+void comm_broadcast_bytes(void* dev, size_t bytes, int root, cudaStream_t s) {
+  if (!g_comm.active() || bytes == 0) return;
+  nccl_check(api().Broadcast(dev, dev, bytes, ncclChar, root, static_cast<ncclComm_t>(g_comm.nccl), s),
+             "ncclBroadcast");
+}
+
+void comm_group_start() {
+  if (g_comm.active()) nccl_check(api().GroupStart(), "ncclGroupStart");
+}
+void comm_group_end() {
+  if (g_comm.active()) nccl_check(api().GroupEnd(), "ncclGroupEnd");
+}
+
+// Rows are dealt in equal chunks of ceil(n / world): every rank but the last owns a full chunk, so
+// an in-place all-gather of fixed-size chunks reproduces the global row order.
+void row_partition(u64 n, int world, int rank, u64& begin, u64& end) {
+  u64 chunk = (n + (u64)world - 1) / (u64)world;
+  begin = std::min(n, chunk * (u64)rank);
+  end = std::min(n, begin + chunk);
+}
+
+}  // namespace sped

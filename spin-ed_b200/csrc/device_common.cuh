@@ -1,0 +1,80 @@
+// device_common.cuh -- helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "internal.h"
+
+namespace sped {
+
+constexpr int kThreads = 256;
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of it
+
+inline int persistent_grid(u64 work_items, int threads, int blocks_per_sm) {
+  u64 need = (work_items + threads - 1) / threads;
+  u64 cap = (u64)kSmCount * blocks_per_sm;
+  return (int)std::max<u64>(1, std::min<u64>(need, cap));
+}
+
+// Bytes needed to stage a program in shared memory (16-byte aligned sections).
+template <class W>
+inline size_t program_smem_bytes(u32 n_steps, u32 n_ops) {
+  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  return up((size_t)n_steps * sizeof(PermStep)) + up((size_t)n_ops * sizeof(PermOp<W>)) +
+         up((size_t)n_steps * sizeof(std::int32_t));
+}
+
+#if defined(__CUDACC__)
+// Cooperative copy of the program into shared memory; returns a view addressing the copy.
+// Must be called by all threads of the block; ends with __syncthreads().
+template <class W>
+__device__ __forceinline__ ProgramView<W> stage_program(ProgramView<W> g, unsigned char* smem, bool enable) {
+  if (!enable) return g;
+  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  PermStep* steps = reinterpret_cast<PermStep*>(smem);
+  PermOp<W>* ops = reinterpret_cast<PermOp<W>*>(smem + up((size_t)g.n_steps * sizeof(PermStep)));
+  std::int32_t* phase = reinterpret_cast<std::int32_t*>(reinterpret_cast<unsigned char*>(ops) +
+                                                        up((size_t)g.n_ops * sizeof(PermOp<W>)));
+  for (u32 i = threadIdx.x; i < g.n_steps; i += blockDim.x) {
+    steps[i] = g.steps[i];
+    phase[i] = g.phase[i];
+  }
+  for (u32 i = threadIdx.x; i < g.n_ops; i += blockDim.x) ops[i] = g.ops[i];
+  __syncthreads();
+  ProgramView<W> v = g;
+  v.steps = steps;
+  v.ops = ops;
+  v.phase = phase;
+  return v;
+}
+
+// Index of representative `rep` in the sorted array, or ~0 if absent.
+__device__ __forceinline__ u64 lookup_index(BasisIndex const& ix, u64 rep) {
+  if (ix.direct) return rep;
+  u64 prefix = rep >> ix.bucket_shift;
+  if (prefix >= ix.bucket_count) return ~0ull;
+  u64 lo, hi;
+  if (ix.bucket_wide) {
+    u64 const* b = static_cast<u64 const*>(ix.bucket);
+    lo = __ldg(b + prefix);
+    hi = __ldg(b + prefix + 1);
+  } else {
+    u32 const* b = static_cast<u32 const*>(ix.bucket);
+    lo = __ldg(b + prefix);
+    hi = __ldg(b + prefix + 1);
+  }
+  // branch-light binary search for the first element >= rep in [lo, hi)
+  while (lo < hi) {
+    u64 mid = lo + ((hi - lo) >> 1);
+    u64 v = __ldg(ix.reps + mid);
+    if (v < rep) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo < ix.n_states && __ldg(ix.reps + lo) == rep) {
+    // lo may have run to the end of the bucket; equality settles membership
+    return lo;
+  }
+  return ~0ull;
+}
+#endif
+
+}  // namespace sped

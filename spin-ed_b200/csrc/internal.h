@@ -1,0 +1,240 @@
+// internal.h -- host-side object model of libsped (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sped.h"
+#include "permprog.h"
+
+namespace sped {
+
+using u64 = std::uint64_t;
+using i64 = std::int64_t;
+using u32 = std::uint32_t;
+using cplx = std::complex<double>;
+
+extern bool g_logging;
+extern std::uint64_t g_launches;
+#define SPED_LOG(...)                               \
+  do {                                              \
+    if (::sped::g_logging) {                        \
+      std::fprintf(stderr, "[sped] " __VA_ARGS__);  \
+      std::fprintf(stderr, "\n");                   \
+    }                                               \
+  } while (0)
+
+struct Error {
+  int code;
+  std::string what;
+};
+[[noreturn]] void fail(int code, std::string what);
+void cuda_check(cudaError_t e, char const* expr, char const* file, int line);
+#define CUDA_CHECK(expr) ::sped::cuda_check((expr), #expr, __FILE__, __LINE__)
+#define KERNEL_LAUNCHED() (++::sped::g_launches)
+
+// Runs fn(), mapping exceptions to status codes; remembers the message for ls_error_to_string.
+int guarded(void (*thunk)(void*), void* ctx);
+template <class F>
+int guard(F&& f) {
+  auto thunk = [](void* p) { (*static_cast<F*>(p))(); };
+  return guarded(thunk, &f);
+}
+
+// ---- simple RAII device buffer ----
+template <class T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceBuffer() = default;
+  explicit DeviceBuffer(size_t n) { alloc(n); }
+  DeviceBuffer(DeviceBuffer const&) = delete;
+  DeviceBuffer& operator=(DeviceBuffer const&) = delete;
+  DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), count(o.count) { o.ptr = nullptr; o.count = 0; }
+  DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+    if (this != &o) { release(); ptr = o.ptr; count = o.count; o.ptr = nullptr; o.count = 0; }
+    return *this;
+  }
+  ~DeviceBuffer() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n) CUDA_CHECK(cudaMalloc((void**)&ptr, n * sizeof(T)));
+    count = n;
+  }
+  void release() {
+    // destructors may run from a GC finalizer at process exit: ignore errors (context may be gone)
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  void upload(T const* host, size_t n) {
+    if (n > count) alloc(n);
+    if (n) CUDA_CHECK(cudaMemcpy(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void upload(std::vector<T> const& v) { upload(v.data(), v.size()); }
+  std::vector<T> download() const {
+    std::vector<T> v(count);
+    if (count) CUDA_CHECK(cudaMemcpy(v.data(), ptr, count * sizeof(T), cudaMemcpyDeviceToHost));
+    return v;
+  }
+};
+
+// ---- symmetry / group (host only; group.cpp) ----
+struct Symmetry {
+  std::vector<unsigned> perm;
+  unsigned sector = 0;
+  unsigned periodicity = 1;
+};
+
+struct GroupElement {
+  std::vector<int> perm;  // (g.x)[i] = x[perm[i]]
+  i64 phase = 0;          // numerator over Group::denom
+};
+
+struct Group {
+  unsigned n = 0;  // permutation length; 0 = trivial group without generators
+  i64 denom = 2;   // common denominator of all phases (always even)
+  std::vector<GroupElement> elems;  // elems[0] = identity
+  bool real_characters() const;
+};
+
+std::shared_ptr<Symmetry> make_symmetry(unsigned n, unsigned const* perm, unsigned sector);
+std::shared_ptr<Group> make_group(std::vector<Symmetry const*> const& gens);
+
+// Compile the traversal of all group elements into a PermProgram (permprog.cpp).
+HostProgram compile_program(Group const& g, unsigned n_spins, int spin_inversion);
+
+// Sector dimension by character-weighted Burnside counting (exact integers); group.cpp.
+u64 burnside_dimension(Group const& g, unsigned n_spins, int hamming_weight, int spin_inversion);
+
+// ---- communicator (comm.cpp) ----
+struct Comm {
+  int world = 1;
+  int rank = 0;
+  void* nccl = nullptr;  // ncclComm_t
+  cudaStream_t stream = nullptr;
+  bool active() const { return world > 1; }
+};
+Comm& comm();
+void comm_unique_id(void* out128);
+void comm_init(int world, int rank, void const* id128);
+void comm_finalize();
+// in-place all-gather: every rank owns chunk `rank` of `chunk_bytes` inside buf (P chunks)
+void comm_allgather_inplace(void* buf, size_t chunk_bytes, cudaStream_t s);
+void comm_allreduce_sum_f64(double* dev, size_t count, cudaStream_t s);
+void comm_allreduce_sum_u64(unsigned long long* dev, size_t count, cudaStream_t s);
+void comm_broadcast_bytes(void* dev, size_t bytes, int root, cudaStream_t s);
+void comm_group_start();
+void comm_group_end();
+void row_partition(u64 n, int world, int rank, u64& begin, u64& end);
+
+// ---- basis (basis.cu) ----
+struct BasisIndex {  // device lookup structures, shared by kernels
+  u64 const* reps = nullptr;         // sorted representatives, global, replicated on every rank
+  std::uint16_t const* stab = nullptr;  // |Stab| per representative (norm^2 = stab / |G'|)
+  void const* bucket = nullptr;      // prefix table: u32 or u64 entries
+  u64 n_states = 0;
+  int bucket_shift = 0;              // prefix = rep >> bucket_shift
+  u32 bucket_count = 0;              // number of prefixes (table has bucket_count + 1 entries)
+  int bucket_wide = 0;               // 1: u64 entries
+  int direct = 0;                    // 1: index == state (no hamming weight, trivial group)
+};
+
+struct Basis {
+  std::shared_ptr<Group> group;
+  unsigned n_spins = 0;
+  int hamming_weight = -1;
+  int spin_inversion = 0;
+  HostProgram program;                // canonicalisation program (empty for the trivial group)
+  DeviceBuffer<unsigned char> d_program;  // packed device image of `program`
+  DeviceBuffer<double> d_norm_table;  // norm_table[s] = sqrt(s / |G'|)
+  DeviceBuffer<double> d_chi_table;   // (cos, sin)(2 pi k / denom), k < denom
+
+  std::mutex mutex;
+  bool built = false;
+  u64 n_states = 0;
+  DeviceBuffer<u64> d_reps;
+  DeviceBuffer<std::uint16_t> d_stab;
+  DeviceBuffer<unsigned char> d_bucket;
+  BasisIndex index;
+  double build_seconds = 0.0;
+  std::shared_ptr<std::vector<u64>> host_reps;  // lazily mirrored for ls_get_states
+  u64 generation = 0;                           // bumped by every (re)build
+
+  bool trivial() const { return group->elems.size() <= 1 && spin_inversion == 0; }
+  u64 group_order() const { return (u64)group->elems.size() * (spin_inversion != 0 ? 2 : 1); }
+  bool use32() const { return n_spins <= 32; }
+  u64 expected_dimension() const;
+  void ensure_device_tables();
+  void build();                                     // K1
+  void adopt(u64 size, u64 const* host_reps_in);    // K1b
+  void finish_build();                              // stabilisers + bucket table
+  std::shared_ptr<std::vector<u64>> states_host();
+  void local_rows(u64& b, u64& e) const { row_partition(n_states, comm().world, comm().rank, b, e); }
+};
+
+std::shared_ptr<Basis> make_basis(std::shared_ptr<Group> g, unsigned n_spins, int hw, int inv);
+
+// ---- interactions / operator (operator.cu) ----
+struct Interaction {
+  int k = 0;
+  std::vector<cplx> matrix;            // row-major 2^k x 2^k
+  std::vector<std::uint16_t> sites;    // count * k
+  bool is_real() const;
+};
+
+struct EighStats {
+  u64 matvecs = 0;
+  int iterations = 0, restarts = 0;
+  double seconds_total = 0, seconds_matvec = 0, seconds_ortho = 0;
+};
+
+struct Operator {
+  std::shared_ptr<Basis> basis;
+  std::vector<Interaction> terms;
+  bool real_matrices = true;
+  bool real_diagonal = true;
+
+  // device image (prepared lazily once the basis is built; re-prepared if the basis is rebuilt)
+  std::mutex mutex;
+  u64 prepared_generation = ~0ull;
+  DeviceBuffer<unsigned char> d_terms;  // packed bonds + matrices (see operator.cu)
+  DeviceBuffer<double> d_diag;          // local rows (real part) [+ imaginary part if !real_diagonal]
+  u64 row_begin = 0, row_end = 0;
+  bool counted = false;
+  u64 n_offdiag = 0;
+  EighStats last_stats;
+
+  bool is_real() const { return real_matrices && basis->group->real_characters(); }
+  void prepare();
+  void matmat_device(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s);
+  void matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs, void* y, u64 ys);
+  void expectation_host(int dtype, u64 size, u64 block, void const* x, u64 xs, cplx* out);
+  void count_elements(u64& rows, u64& offdiag);
+};
+
+std::shared_ptr<Interaction> make_interaction(int k, void const* matrix, unsigned count, std::uint16_t const* sites);
+std::shared_ptr<Operator> make_operator(std::shared_ptr<Basis> b, std::vector<Interaction const*> const& terms);
+
+inline size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case SPED_F32: return 4;
+    case SPED_F64: return 8;
+    case SPED_C64: return 8;
+    case SPED_C128: return 16;
+  }
+  fail(LS_INVALID_DATATYPE, "unknown datatype tag");
+}
+inline bool dtype_is_complex(int dtype) { return dtype == SPED_C64 || dtype == SPED_C128; }
+
+// ---- eigensolver (eigh.cu) ----
+int eigh(Operator& op, int dtype, u64 n_evals, double eps, int max_basis, int max_block, int min_restart,
+         double* evals, void* evecs, double* rnorms, sped_monitor_fn monitor, void* ctx);
+
+}  // namespace sped

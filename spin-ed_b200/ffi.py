@@ -1,0 +1,465 @@
+"""ctypes binding of libsped.so -- the Python mirror of the reference's FFI layer
+(/root/reference/src/SpinED/Internal.hs).  Function and class names follow that module:
+``mkSymmetry``/``Symmetry`` (:99-116), ``mkGroup``/``SymmetryGroup`` (:141-150), ``mkBasis``/
+``SpinBasis`` (:199-228), ``buildBasis`` (:230-236), ``basisGetStates`` (:238-244),
+``getNumberStates`` (:247-254), ``mkInteraction'``/``Interaction`` (:293-362), ``mkOperator``/
+``Operator'`` (:391-402), ``inplaceApply`` (:411-429), ``apply`` (:431-435), ``expectation``
+(:437-452).  Error behaviour is the same: a non-zero status raises ``LatticeSymmetriesException``
+(code, message) (:48-65); argument errors caught before the FFI raise ``SpinEDException``.
+
+There is no CPU fallback: every compute call goes to the CUDA library and fails loudly if the
+library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsped.so")
+_lib = None
+
+F32, F64, C64, C128 = 0, 1, 2, 3
+DTYPE_TAGS = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.complex64): C64, np.dtype(np.complex128): C128}
+TAG_DTYPES = {v: k for k, v in DTYPE_TAGS.items()}
+
+
+class LatticeSymmetriesException(RuntimeError):
+    """Mirror of ``LatticeSymmetriesException {eCode, eMessage}`` (Internal.hs:28-31)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.eCode = code
+        self.eMessage = message
+
+
+class SpinEDException(RuntimeError):
+    """Mirror of ``SpinEDException`` (Internal.hs:33-36)."""
+
+
+class sped_eigh_info(C.Structure):
+    _fields_ = [
+        ("iteration", C.c_int), ("basis_size", C.c_int), ("number_converged", C.c_int), ("number_evals", C.c_int),
+        ("number_matvecs", C.c_uint64), ("evals", C.POINTER(C.c_double)), ("rnorms", C.POINTER(C.c_double)),
+        ("elapsed_seconds", C.c_double),
+    ]
+
+
+class sped_eigh_stats(C.Structure):
+    _fields_ = [
+        ("matvecs", C.c_uint64), ("iterations", C.c_int), ("restarts", C.c_int), ("seconds_total", C.c_double),
+        ("seconds_matvec", C.c_double), ("seconds_ortho", C.c_double),
+    ]
+
+
+MONITOR_FN = C.CFUNCTYPE(C.c_int, C.POINTER(sped_eigh_info), C.c_void_p)
+
+# name -> (restype, argtypes); the list is the contract checked against include/sped.h by the tests
+_vp, _u64, _ci, _cu, _pp = C.c_void_p, C.c_uint64, C.c_int, C.c_uint, C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "ls_error_to_string": (C.c_void_p, [_ci]),
+    "ls_destroy_string": (None, [_vp]),
+    "ls_enable_logging": (None, []),
+    "ls_disable_logging": (None, []),
+    "ls_create_symmetry": (_ci, [_pp, _cu, _vp, _cu]),
+    "ls_destroy_symmetry": (None, [_vp]),
+    "ls_get_sector": (_cu, [_vp]),
+    "ls_get_phase": (C.c_double, [_vp]),
+    "ls_get_periodicity": (_cu, [_vp]),
+    "ls_create_group": (_ci, [_pp, _cu, _vp]),
+    "ls_destroy_group": (None, [_vp]),
+    "ls_get_group_size": (_cu, [_vp]),
+    "ls_create_spin_basis": (_ci, [_pp, _vp, _cu, _ci, _ci]),
+    "ls_destroy_spin_basis": (None, [_vp]),
+    "ls_build": (_ci, [_vp]),
+    "ls_build_unsafe": (_ci, [_vp, _u64, _vp]),
+    "ls_get_number_states": (_ci, [_vp, C.POINTER(_u64)]),
+    "ls_get_states": (_ci, [_pp, _vp]),
+    "ls_states_get_data": (_vp, [_vp]),
+    "ls_states_get_size": (_u64, [_vp]),
+    "ls_destroy_states": (None, [_vp]),
+    "ls_create_interaction1": (_ci, [_pp, _vp, _cu, _vp]),
+    "ls_create_interaction2": (_ci, [_pp, _vp, _cu, _vp]),
+    "ls_create_interaction3": (_ci, [_pp, _vp, _cu, _vp]),
+    "ls_create_interaction4": (_ci, [_pp, _vp, _cu, _vp]),
+    "ls_interaction_is_real": (C.c_bool, [_vp]),
+    "ls_destroy_interaction": (None, [_vp]),
+    "ls_create_operator": (_ci, [_pp, _vp, _cu, _vp]),
+    "ls_destroy_operator": (None, [_vp]),
+    "ls_operator_is_real": (C.c_bool, [_vp]),
+    "ls_operator_matmat": (_ci, [_vp, _ci, _u64, _u64, _vp, _u64, _vp, _u64]),
+    "ls_operator_expectation": (_ci, [_vp, _ci, _u64, _u64, _vp, _u64, _vp]),
+    "sped_version": (C.c_char_p, []),
+    "sped_device_count": (_ci, [C.POINTER(_ci)]),
+    "sped_set_device": (_ci, [_ci]),
+    "sped_kernel_launches": (_u64, []),
+    "sped_comm_unique_id": (_ci, [_vp]),
+    "sped_comm_init": (_ci, [_ci, _ci, _vp]),
+    "sped_comm_finalize": (_ci, []),
+    "sped_comm_rank": (_ci, []),
+    "sped_comm_size": (_ci, []),
+    "sped_row_partition": (None, [_u64, _ci, _ci, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sped_basis_build_seconds": (_ci, [_vp, C.POINTER(C.c_double)]),
+    "sped_basis_local_rows": (_ci, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sped_basis_device_states": (_ci, [_vp, _pp]),
+    "sped_basis_norms": (_ci, [_vp, _vp]),
+    "sped_basis_state_info": (_ci, [_vp, _u64, _vp, _vp, _vp, _vp]),
+    "sped_basis_program_stats": (_ci, [_vp, C.POINTER(_cu), C.POINTER(_cu), C.POINTER(_cu)]),
+    "sped_operator_matmat_device": (_ci, [_vp, _ci, _u64, _vp, _u64, _vp, _u64, _vp]),
+    "sped_operator_count_elements": (_ci, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sped_operator_diagonal": (_ci, [_vp, _vp]),
+    "sped_eigh": (_ci, [_vp, _ci, _u64, C.c_double, _ci, _ci, _ci, _vp, _vp, _vp, MONITOR_FN, _vp]),
+    "sped_eigh_last_stats": (_ci, [_vp, C.POINTER(sped_eigh_stats)]),
+    "sped_selftest_small_eigh": (_ci, [_ci, _vp, _vp, _vp]),
+    "sped_selftest_program": (_ci, [_vp, _u64, _vp, _vp, _vp, _vp]),
+    "sped_selftest_burnside": (_ci, [_vp, C.POINTER(_u64)]),
+}
+
+
+def lib():
+    """Load libsped.so (built in-tree by ``__graft_entry__.build()``); no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()')"
+            )
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def getErrorMessage(code: int) -> str:
+    p = lib().ls_error_to_string(code)
+    try:
+        return C.cast(p, C.c_char_p).value.decode()
+    finally:
+        lib().ls_destroy_string(p)
+
+
+def checkStatus(code: int):
+    if code != 0:
+        raise LatticeSymmetriesException(code, getErrorMessage(code))
+
+
+def _mkObject(f):
+    out = C.c_void_p()
+    checkStatus(f(C.byref(out)))
+    return out
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+
+    def __del__(self):
+        p, self._ptr = getattr(self, "_ptr", None), None
+        if p and _lib is not None:
+            getattr(_lib, self._destroy)(p)
+
+
+class Symmetry(_Handle):
+    _destroy = "ls_destroy_symmetry"
+
+
+def mkSymmetry(permutation, sector: int) -> Symmetry:
+    if any(int(p) < 0 for p in permutation):
+        raise SpinEDException(f"invalid permutation: {list(permutation)}; indices must be non-negative")
+    if sector < 0:
+        raise SpinEDException(f"invalid sector: {sector}; expected a non-negative number")
+    p = np.ascontiguousarray(permutation, dtype=np.uint32)
+    return Symmetry(_mkObject(lambda out: lib().ls_create_symmetry(out, len(p), p.ctypes.data, sector)))
+
+
+def getSector(s: Symmetry) -> int:
+    return int(lib().ls_get_sector(s._ptr))
+
+
+def getPeriodicity(s: Symmetry) -> int:
+    return int(lib().ls_get_periodicity(s._ptr))
+
+
+def getPhase(s: Symmetry) -> float:
+    return float(lib().ls_get_phase(s._ptr))
+
+
+class SymmetryGroup(_Handle):
+    _destroy = "ls_destroy_group"
+
+
+def mkGroup(symmetries) -> SymmetryGroup:
+    arr = (C.c_void_p * max(1, len(symmetries)))(*[s._ptr for s in symmetries])
+    return SymmetryGroup(_mkObject(lambda out: lib().ls_create_group(out, len(symmetries), arr)))
+
+
+def getGroupSize(g: SymmetryGroup) -> int:
+    return int(lib().ls_get_group_size(g._ptr))
+
+
+class SpinBasis(_Handle):
+    _destroy = "ls_destroy_spin_basis"
+
+
+def mkBasis(group: SymmetryGroup, numberSpins: int, hammingWeight=None, spinInversion=None) -> SpinBasis:
+    if numberSpins <= 0:
+        raise SpinEDException(f"invalid number of spins: {numberSpins}; expected a positive number")
+    if hammingWeight is not None and hammingWeight < 0:
+        raise SpinEDException(f"invalid Hamming weight: {hammingWeight}; expected a non-negative number")
+    if spinInversion is not None and spinInversion not in (1, -1):
+        raise SpinEDException(f"invalid value for spin inversion: {spinInversion}; expected either -1 or +1")
+    hw = -1 if hammingWeight is None else hammingWeight
+    inv = 0 if spinInversion is None else spinInversion
+    b = SpinBasis(_mkObject(lambda out: lib().ls_create_spin_basis(out, group._ptr, numberSpins, hw, inv)))
+    b.number_spins = numberSpins
+    return b
+
+
+def buildBasis(basis: SpinBasis, representatives=None):
+    if representatives is None:
+        checkStatus(lib().ls_build(basis._ptr))
+    else:
+        r = np.ascontiguousarray(representatives, dtype=np.uint64)
+        checkStatus(lib().ls_build_unsafe(basis._ptr, len(r), r.ctypes.data))
+
+
+def getNumberStates(basis: SpinBasis) -> int:
+    out = C.c_uint64(0)
+    checkStatus(lib().ls_get_number_states(basis._ptr, C.byref(out)))
+    return int(out.value)
+
+
+class _States(_Handle):
+    _destroy = "ls_destroy_states"
+
+
+def basisGetStates(basis: SpinBasis) -> np.ndarray:
+    """Zero-copy view of the representatives; the ``ls_states`` object lives as long as the array."""
+    st = _States(_mkObject(lambda out: lib().ls_get_states(out, basis._ptr)))
+    n = int(lib().ls_states_get_size(st._ptr))
+    if n == 0:
+        return np.zeros(0, dtype=np.uint64)
+    buf = (C.c_uint64 * n).from_address(lib().ls_states_get_data(st._ptr))
+    arr = np.frombuffer(buf, dtype=np.uint64).view(_StatesArray)
+    arr._owner = st  # the ls_states object is destroyed when the last view of the array goes away
+    arr.flags.writeable = False
+    return arr
+
+
+class _StatesArray(np.ndarray):
+    _owner = None
+
+
+class Interaction(_Handle):
+    _destroy = "ls_destroy_interaction"
+
+
+def toMatrix(dim: int, rows) -> np.ndarray:
+    rows = [list(r) for r in rows]
+    if len(rows) != dim or any(len(r) != dim for r in rows):
+        raise SpinEDException(f"invalid matrix: {rows}; expected a square matrix of dimension {dim}")
+    out = np.zeros((dim, dim), dtype=np.complex128)
+    for i, r in enumerate(rows):
+        for j, v in enumerate(r):
+            out[i, j] = complex(*v) if isinstance(v, (list, tuple)) else complex(v)
+    return out
+
+
+def mkInteraction(matrix, sites) -> Interaction:
+    """``mkInteraction'`` for site tuples of uniform length 1..4 (Internal.hs:293-362)."""
+    sites = [list(s) if isinstance(s, (list, tuple)) else [s] for s in sites]
+    if not sites:
+        raise SpinEDException("zero-point interactions (i.e. constant factors) are not supported")
+    n = len(sites[0])
+    if n not in (1, 2, 3, 4):
+        raise SpinEDException(f"currently only 1-, 2-, 3-, and 4-point interactions are supported, but received n={n}")
+    if any(len(s) != n for s in sites):
+        raise SpinEDException(f"invalid sites: {sites}; expected an array of length-{n} tuples")
+    m = np.ascontiguousarray(toMatrix(1 << n, matrix))
+    flat = [int(v) for s in sites for v in s]
+    if any(v < 0 for v in flat):
+        raise SpinEDException("site indices must be all non-negative numbers")
+    s16 = np.ascontiguousarray(flat, dtype=np.uint16)
+    fn = getattr(lib(), f"ls_create_interaction{n}")
+    return Interaction(_mkObject(lambda out: fn(out, m.ctypes.data, len(sites), s16.ctypes.data)))
+
+
+def isRealInteraction(t: Interaction) -> bool:
+    return bool(lib().ls_interaction_is_real(t._ptr))
+
+
+class Operator(_Handle):
+    """``Operator'`` (Internal.hs:369)."""
+
+    _destroy = "ls_destroy_operator"
+
+
+def mkOperator(basis: SpinBasis, terms) -> Operator:
+    arr = (C.c_void_p * max(1, len(terms)))(*[t._ptr for t in terms])
+    op = Operator(_mkObject(lambda out: lib().ls_create_operator(out, basis._ptr, len(terms), arr)))
+    op.basis = basis
+    return op
+
+
+def isOperatorReal(op: Operator) -> bool:
+    return bool(lib().ls_operator_is_real(op._ptr))
+
+
+def _block(x: np.ndarray):
+    """Column-major (size, blockSize) view + stride, like primme-hs's ``Block``."""
+    x = np.asarray(x)
+    if x.dtype not in DTYPE_TAGS:
+        raise SpinEDException(f"unsupported datatype {x.dtype}")
+    X = x.reshape(len(x), -1)
+    if not X.flags.f_contiguous:
+        X = np.asfortranarray(X)
+    return X, X.shape[0], X.shape[1], max(X.strides[1] // X.itemsize, X.shape[0]) if X.shape[1] > 1 else X.shape[0]
+
+
+def inplaceApply(op: Operator, x: np.ndarray, y: np.ndarray):
+    X, size, block, xs = _block(x)
+    if y.shape != x.shape or y.dtype != x.dtype:
+        raise SpinEDException(f"dimensions of x and y do not match: {x.shape} != {y.shape}")
+    if not (y.flags.f_contiguous or y.ndim == 1):
+        raise SpinEDException("y must be column-major")
+    checkStatus(lib().ls_operator_matmat(op._ptr, DTYPE_TAGS[X.dtype], size, block, X.ctypes.data, xs, y.ctypes.data, size))
+
+
+def apply(op: Operator, x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x)
+    y = np.zeros(x.shape, dtype=x.dtype, order="F")
+    inplaceApply(op, x, y)
+    return y
+
+
+def expectation(op: Operator, x: np.ndarray) -> np.ndarray:
+    X, size, block, xs = _block(x)
+    out = np.zeros(block, dtype=np.complex128)
+    checkStatus(lib().ls_operator_expectation(op._ptr, DTYPE_TAGS[X.dtype], size, block, X.ctypes.data, xs, out.ctypes.data))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# group B: device-resident solver and plumbing
+# ---------------------------------------------------------------------------------------------
+def deviceCount() -> int:
+    out = C.c_int(0)
+    checkStatus(lib().sped_device_count(C.byref(out)))
+    return out.value
+
+
+def setDevice(i: int):
+    checkStatus(lib().sped_set_device(i))
+
+
+def kernelLaunches() -> int:
+    return int(lib().sped_kernel_launches())
+
+
+def rowPartition(n: int, world: int, rank: int):
+    b, e = C.c_uint64(0), C.c_uint64(0)
+    lib().sped_row_partition(n, world, rank, C.byref(b), C.byref(e))
+    return int(b.value), int(e.value)
+
+
+def commUniqueId() -> bytes:
+    buf = C.create_string_buffer(128)
+    checkStatus(lib().sped_comm_unique_id(buf))
+    return buf.raw
+
+
+def commInit(world: int, rank: int, unique_id: bytes):
+    checkStatus(lib().sped_comm_init(world, rank, C.create_string_buffer(unique_id, 128)))
+
+
+def commFinalize():
+    checkStatus(lib().sped_comm_finalize())
+
+
+def basisBuildSeconds(basis: SpinBasis) -> float:
+    out = C.c_double(0)
+    checkStatus(lib().sped_basis_build_seconds(basis._ptr, C.byref(out)))
+    return out.value
+
+
+def basisLocalRows(basis: SpinBasis):
+    b, e = C.c_uint64(0), C.c_uint64(0)
+    checkStatus(lib().sped_basis_local_rows(basis._ptr, C.byref(b), C.byref(e)))
+    return int(b.value), int(e.value)
+
+
+def basisNorms(basis: SpinBasis) -> np.ndarray:
+    out = np.zeros(getNumberStates(basis), dtype=np.float64)
+    checkStatus(lib().sped_basis_norms(basis._ptr, out.ctypes.data))
+    return out
+
+
+def basisStateInfo(basis: SpinBasis, states):
+    s = np.ascontiguousarray(states, dtype=np.uint64)
+    reps = np.zeros(len(s), dtype=np.uint64)
+    chars = np.zeros(len(s), dtype=np.complex128)
+    norms = np.zeros(len(s), dtype=np.float64)
+    checkStatus(lib().sped_basis_state_info(basis._ptr, len(s), s.ctypes.data, reps.ctypes.data, chars.ctypes.data, norms.ctypes.data))
+    return reps, chars, norms
+
+
+def basisProgramStats(basis: SpinBasis):
+    a, b, c = C.c_uint(0), C.c_uint(0), C.c_uint(0)
+    checkStatus(lib().sped_basis_program_stats(basis._ptr, C.byref(a), C.byref(b), C.byref(c)))
+    return {"steps": a.value, "rotate_mask_ops": b.value, "delta_swap_ops": c.value}
+
+
+def operatorMatmatDevice(op: Operator, dtype_tag: int, block: int, x_ptr: int, x_stride: int, y_ptr: int, y_stride: int, stream: int = 0):
+    checkStatus(lib().sped_operator_matmat_device(op._ptr, dtype_tag, block, x_ptr, x_stride, y_ptr, y_stride, stream))
+
+
+def operatorCountElements(op: Operator):
+    r, e = C.c_uint64(0), C.c_uint64(0)
+    checkStatus(lib().sped_operator_count_elements(op._ptr, C.byref(r), C.byref(e)))
+    return int(r.value), int(e.value)
+
+
+def operatorDiagonal(op: Operator) -> np.ndarray:
+    b, e = basisLocalRows(op.basis)
+    out = np.zeros(e - b, dtype=np.float64)
+    checkStatus(lib().sped_operator_diagonal(op._ptr, out.ctypes.data))
+    return out
+
+
+def eigh(op: Operator, dtype, numEvals=1, eps=0.0, maxBasisSize=0, maxBlockSize=0, minRestartSize=0, monitor=None,
+         want_vectors=True):
+    """Replacement of ``Numeric.PRIMME.eigh`` (SpinED.hs:404): -> (evals, evecs (N, k) column-major, rnorms)."""
+    dtype = np.dtype(dtype)
+    tag = DTYPE_TAGS[dtype]
+    n = getNumberStates(op.basis)
+    evals = np.zeros(numEvals, dtype=np.float64)
+    rnorms = np.zeros(numEvals, dtype=np.float64)
+    evecs = np.zeros((n, numEvals), dtype=dtype, order="F") if want_vectors else None
+
+    def _cb(info_p, _ctx):
+        info = info_p.contents
+        k = info.number_evals
+        return int(bool(monitor({
+            "iteration": info.iteration, "basis_size": info.basis_size, "number_converged": info.number_converged,
+            "number_matvecs": info.number_matvecs, "evals": [info.evals[i] for i in range(k)],
+            "rnorms": [info.rnorms[i] for i in range(k)], "elapsed_seconds": info.elapsed_seconds,
+        })))
+
+    cb = MONITOR_FN(_cb) if monitor is not None else C.cast(None, MONITOR_FN)
+    rc = lib().sped_eigh(op._ptr, tag, numEvals, eps, maxBasisSize, maxBlockSize, minRestartSize, evals.ctypes.data,
+                         evecs.ctypes.data if want_vectors else None, rnorms.ctypes.data, cb, None)
+    checkStatus(rc)
+    return evals, evecs, rnorms
+
+
+def eighLastStats(op: Operator) -> dict:
+    st = sped_eigh_stats()
+    checkStatus(lib().sped_eigh_last_stats(op._ptr, C.byref(st)))
+    return {f: getattr(st, f) for f, _ in st._fields_}

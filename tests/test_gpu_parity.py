@@ -1,0 +1,280 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same inputs.  Bar: representatives bit-exact; matvec <= 1e-12 relative L2 (f64/c128 storage;
+f32/c64 storage is compared at 5e-6, the rounding of the stored vectors); eigenvalues <= 1e-10
+relative; residuals <= 1e-8 (relative to |E0|)."""
+import numpy as np
+import pytest
+
+from helpers import SMALL_DECKS, extra_configs, oracle_problem, product_problem, splitmix_vector
+from spin_ed_b200 import decks, ffi
+
+pytestmark = pytest.mark.gpu
+
+ALL_SMALL = {**{n: None for n in SMALL_DECKS}, **extra_configs()}
+
+
+def _cfg(name):
+    return decks.load(name) if ALL_SMALL.get(name) is None and name not in extra_configs() else extra_configs()[name]
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_device_present_and_library_loaded():
+    assert ffi.deviceCount() >= 1
+    assert b"sm_100a" in ffi.lib().sped_version()
+
+
+@pytest.mark.parametrize("name", sorted(ALL_SMALL))
+def test_representatives_bit_exact_small(oracle, name):
+    cfg = _cfg(name)
+    ob, _ = oracle_problem(oracle, cfg)
+    ob.build()
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    assert ffi.getNumberStates(uc.cBasis) == ob.number_states
+    got = ffi.basisGetStates(uc.cBasis)
+    assert got.dtype == np.uint64 and np.array_equal(got, ob.states)
+    assert np.array_equal(ffi.basisNorms(uc.cBasis), ob.norms)
+
+
+def test_known_answer_readme_ring():
+    # /root/reference/README.md:37-95 -- 4-spin ring: 16 representatives, E0 = -8
+    uc = product_problem(decks.load("heisenberg_chain_4"))
+    ffi.buildBasis(uc.cBasis)
+    assert np.array_equal(ffi.basisGetStates(uc.cBasis), np.arange(16, dtype=np.uint64))
+    ev, vecs, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 1)
+    assert abs(ev[0] + 8.0) < 1e-10 and rn[0] < 1e-8
+    assert vecs.shape == (16, 1)
+
+
+def test_known_answer_chain_10_representatives():
+    uc = product_problem(decks.load("heisenberg_chain_10"))
+    ffi.buildBasis(uc.cBasis)
+    assert list(ffi.basisGetStates(uc.cBasis)) == [31, 47, 55, 87, 91, 93, 103, 107, 155, 171, 173, 179, 341]
+
+
+@pytest.mark.parametrize("name", sorted(ALL_SMALL))
+@pytest.mark.parametrize("block", [1, 3])
+def test_matvec_matches_oracle_small(oracle, name, block):
+    cfg = _cfg(name)
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    op = uc.cHamiltonian.operatorObject
+    assert ffi.isOperatorReal(op) == oop.is_real
+    n = ob.number_states
+    dtypes = [np.float64, np.float32] if oop.is_real else []
+    dtypes += [np.complex128, np.complex64]
+    for dt in dtypes:
+        x = np.asfortranarray(np.stack([splitmix_vector(n, 0x5EED0001 + c, dt) for c in range(block)], axis=1))
+        want = oop.matmat(x.astype(np.complex128 if np.dtype(dt).kind == "c" else np.float64))
+        got = ffi.apply(op, x)
+        tol = 1e-12 if np.dtype(dt).itemsize // (2 if np.dtype(dt).kind == "c" else 1) == 8 else 5e-6
+        assert got.dtype == np.dtype(dt)
+        assert rel(got, want) < tol, (name, dt, rel(got, want))
+    rows, E = ffi.operatorCountElements(op)
+    assert rows == n and E == oop.count_offdiag()
+    if not oop.is_real:
+        with pytest.raises(ffi.LatticeSymmetriesException) as e:
+            ffi.apply(op, np.zeros(n, dtype=np.float64))
+        assert e.value.eCode == 18
+
+
+def test_matvec_strided_blocks_and_dimension_mismatch(oracle):
+    cfg = decks.load("heisenberg_square_4x4")
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    op = uc.cHamiltonian.operatorObject
+    n = ob.number_states
+    big = np.zeros((n + 5, 4), order="F")
+    big[:n, :] = np.stack([splitmix_vector(n, 7 + c) for c in range(4)], axis=1)
+    x = big[:n, :]  # column stride n + 5
+    y = np.zeros((n, 4), order="F")
+    ffi.checkStatus(ffi.lib().ls_operator_matmat(op._ptr, ffi.F64, n, 4, x.ctypes.data, n + 5, y.ctypes.data, n))
+    assert rel(y, oop.matmat(np.asfortranarray(x))) < 1e-12
+    with pytest.raises(ffi.LatticeSymmetriesException) as e:
+        ffi.apply(op, np.zeros(n + 1))
+    assert e.value.eCode == 19
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_square_4x4", "chain_8_k1_complex", "ring_4site_nosym"])
+def test_expectation_matches_oracle(oracle, name):
+    cfg = _cfg(name)
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    n = ob.number_states
+    dt = np.float64 if oop.is_real else np.complex128
+    x = np.asfortranarray(np.stack([splitmix_vector(n, 3 + c, dt) for c in range(2)], axis=1))
+    got = ffi.expectation(uc.cHamiltonian.operatorObject, x)
+    want = oop.expectation(x)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_build_unsafe_adopts_representatives(oracle):
+    cfg = decks.load("heisenberg_square_4x4")
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis, ob.states)  # resume path, /root/reference/src/SpinED.hs:319-331
+    assert ffi.getNumberStates(uc.cBasis) == 107
+    x = splitmix_vector(107)
+    assert rel(ffi.apply(uc.cHamiltonian.operatorObject, x), oracle.Operator(ob, terms).matmat(x)) < 1e-12
+    bad = ob.states.copy()
+    bad[3] = bad[3] ^ np.uint64(3)  # no longer an orbit minimum (or unsorted)
+    uc2 = product_problem(cfg)
+    with pytest.raises(ffi.LatticeSymmetriesException):
+        ffi.buildBasis(uc2.cBasis, bad)
+
+
+def test_operator_created_before_build_sees_later_build(oracle):
+    # /root/reference/src/SpinED.hs:243-248 creates operators before app/Main.hs:22 builds the basis
+    cfg = decks.load("heisenberg_chain_10")
+    uc = product_problem(cfg)
+    op = uc.cHamiltonian.operatorObject
+    with pytest.raises(ffi.LatticeSymmetriesException) as e:
+        ffi.apply(op, np.zeros(13))
+    assert e.value.eCode == 14
+    ffi.buildBasis(uc.cBasis)
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    x = splitmix_vector(13)
+    assert rel(ffi.apply(op, x), oracle.Operator(ob, terms).matmat(x)) < 1e-12
+
+
+def test_handles_survive_any_destroy_order(oracle):
+    import gc
+
+    cfg = decks.load("heisenberg_chain_10")
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    states = ffi.basisGetStates(uc.cBasis)
+    op = uc.cHamiltonian.operatorObject
+    del uc
+    gc.collect()
+    assert list(states[:3]) == [31, 47, 55]
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    x = splitmix_vector(13)
+    assert rel(ffi.apply(op, x), oracle.Operator(ob, terms).matmat(x)) < 1e-12
+
+
+@pytest.mark.parametrize("name,k", [("heisenberg_chain_10", 1), ("heisenberg_kagome_12", 4), ("heisenberg_square_4x4", 2),
+                                    ("heisenberg_triangular_19", 2), ("chain_8_k1_complex", 2), ("chain_12_full_sym", 3)])
+def test_eigenpairs_match_oracle_dense(oracle, name, k):
+    cfg = _cfg(name)
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    n = ob.number_states
+    if n <= 1500:
+        want = np.linalg.eigvalsh(oop.to_dense())[:k]
+    else:
+        import scipy.sparse.linalg as sla
+
+        dt = np.float64 if oop.is_real else np.complex128
+        A = sla.LinearOperator((n, n), matvec=lambda v: oop.matmat(np.ascontiguousarray(v, dtype=dt)), dtype=dt)
+        want = np.sort(sla.eigsh(A, k=k + 2, which="SA", tol=1e-12)[0])[:k]
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    op = uc.cHamiltonian.operatorObject
+    dt = np.float64 if ffi.isOperatorReal(op) else np.complex128
+    ev, vecs, rn = ffi.eigh(op, dt, k)
+    scale = max(1.0, abs(want[0]))
+    assert np.all(np.abs(ev - want) <= 1e-10 * scale), (ev, want)
+    assert np.all(rn <= 1e-8 * scale)
+    # eigenvectors: residual of what was returned, checked with the oracle's operator
+    hv = oop.matmat(np.asfortranarray(vecs))
+    for i in range(k):
+        assert np.linalg.norm(hv[:, i] - ev[i] * vecs[:, i]) <= 1e-8 * scale
+        assert abs(np.linalg.norm(vecs[:, i]) - 1) < 1e-10
+    # expectation of H in the eigenvectors reproduces the eigenvalues (observables path)
+    ex = ffi.expectation(op, vecs)
+    assert np.allclose(ex.real, ev, atol=1e-9 * scale) and np.allclose(ex.imag, 0, atol=1e-9)
+
+
+def test_eigh_small_basis_restarts_like_the_40_spin_decks(oracle):
+    # chain_40/42 run with max_primme_basis_size 3/4: exercise restarts on a small symmetric chain
+    cfg = decks.chain(16, 8, 1, (0, 0))
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    want = np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())[0]
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    op = uc.cHamiltonian.operatorObject
+    ev, _, rn = ffi.eigh(op, np.float64, 1, maxBasisSize=3)
+    st = ffi.eighLastStats(op)
+    assert abs(ev[0] - want) <= 1e-10 * abs(want) and rn[0] <= 1e-8 * abs(want)
+    assert st["restarts"] > 0 and st["matvecs"] >= st["iterations"]
+
+
+def test_eigh_float32_storage(oracle):
+    cfg = decks.load("heisenberg_square_4x4")  # the deck asks for float32 (SpinED.hs:344-352)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    ev, vecs, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float32, 2, maxBasisSize=20, maxBlockSize=4)
+    assert vecs.dtype == np.float32
+    assert abs(ev[0] + 44.9139328337) < 2e-3  # storage-precision bound, float64 parity is tested above
+
+
+def test_monitor_callback_and_abort():
+    uc = product_problem(decks.load("heisenberg_kagome_12"))
+    ffi.buildBasis(uc.cBasis)
+    seen = []
+    ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 1, monitor=lambda info: seen.append(info) or False)
+    assert seen and seen[-1]["number_converged"] == 1 and seen[0]["iteration"] == 0
+
+
+@pytest.mark.parametrize("name", ["heisenberg_square_5x5", "heisenberg_chain_24", "xxz_triangular_19", "heisenberg_pyrochlore_32"])
+def test_mid_size_decks_bit_exact_and_matvec(oracle, name):
+    cfg = decks.load(name)
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    assert np.array_equal(ffi.basisGetStates(uc.cBasis), ob.states)
+    n = ob.number_states
+    dt = np.float64 if oop.is_real else np.complex128
+    x = splitmix_vector(n, 0x5EED0001, dt)
+    x /= np.linalg.norm(x)
+    got = ffi.apply(uc.cHamiltonian.operatorObject, x)
+    want, E = oop.matmat(x, count=True)
+    assert rel(got, want) < 1e-12
+    assert ffi.operatorCountElements(uc.cHamiltonian.operatorObject) == (n, E)
+
+
+def test_full_size_6x6_properties():
+    """BASELINE full size (no oracle run: minutes of CPU): size-independent properties."""
+    uc = product_problem(decks.load("heisenberg_square_6x6"))
+    ffi.buildBasis(uc.cBasis)
+    n = ffi.getNumberStates(uc.cBasis)
+    assert n == 15804956  # Burnside / literature value
+    reps = ffi.basisGetStates(uc.cBasis)
+    assert np.all(reps[1:] > reps[:-1])
+    pop = np.zeros(n, dtype=np.uint8)
+    for b in range(36):
+        pop += ((reps >> np.uint64(b)) & np.uint64(1)).astype(np.uint8)
+    assert np.all(pop == 18)
+    # every representative is its own representative with non-zero norm (idempotence of canonicalise)
+    sample = reps[:: max(1, n // 4096)]
+    r2, chi, norms = ffi.basisStateInfo(uc.cBasis, sample)
+    assert np.array_equal(r2, sample) and np.all(norms > 0) and np.allclose(chi, 1)
+    # Hermiticity: <u, H v> == <H u, v>
+    op = uc.cHamiltonian.operatorObject
+    u = splitmix_vector(n, 11)
+    v = splitmix_vector(n, 12)
+    hu, hv = ffi.apply(op, u), ffi.apply(op, v)
+    assert abs(np.dot(u, hv) - np.dot(hu, v)) <= 1e-10 * abs(np.dot(u, hv))
+    # linearity
+    w = ffi.apply(op, 2.0 * u - 3.0 * v)
+    assert rel(w, 2.0 * hu - 3.0 * hv) < 1e-12

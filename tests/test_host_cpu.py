@@ -1,0 +1,201 @@
+"""CPU-side tests (-m "not gpu"): the library loads and exports the ABI, the host logic of the
+product (group closure, error behaviour, Burnside dimension, canonicalisation-program compiler,
+projected eigen-solver, row partition) agrees with the oracle / numpy."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import SMALL_DECKS, extra_configs, oracle_problem, product_problem
+from spin_ed_b200 import config, decks, ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = set()
+    for hdr in ("sped.h", "sped_selftest.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b((?:ls|sped)_[a-z0-9_]+)\s*\(", text))
+    declared -= {"sped_monitor_fn"}
+    assert len(declared) >= 50
+    L = C.CDLL(ffi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(ffi.SIGNATURES), declared ^ set(ffi.SIGNATURES)
+
+
+def test_symmetry_semantics_of_reference_spec():
+    # /root/reference/test/Spec.hs:38-43
+    s = ffi.mkSymmetry([3, 2, 1, 0], 0)
+    assert ffi.getSector(s) == 0 and ffi.getPeriodicity(s) == 2 and ffi.getPhase(s) == 0.0
+    with pytest.raises(ffi.LatticeSymmetriesException):
+        ffi.mkSymmetry([4, 3, 4, 1], 0)
+    with pytest.raises(ffi.LatticeSymmetriesException):
+        ffi.mkSymmetry([4, 3, 2, 1, 0], 3)
+    with pytest.raises(ffi.SpinEDException):
+        ffi.mkSymmetry([1, -1, 0], 0)
+    assert ffi.getPhase(ffi.mkSymmetry([1, 2, 3, 0], 1)) == 0.25
+
+
+def test_group_semantics_of_reference_spec():
+    # /root/reference/test/Spec.hs:72-79 (the spin flip generator of that stale test is now the
+    # basis' spin_inversion; the lattice part D4 has 8 elements)
+    s1 = ffi.mkSymmetry([3, 2, 1, 0], 0)
+    s2 = ffi.mkSymmetry([1, 2, 3, 0], 0)
+    s2b = ffi.mkSymmetry([1, 2, 3, 0], 1)
+    assert ffi.getGroupSize(ffi.mkGroup([s1, s2])) == 8
+    with pytest.raises(ffi.LatticeSymmetriesException) as e:
+        ffi.mkGroup([s1, s2b])
+    assert e.value.eCode == 11
+    assert ffi.getGroupSize(ffi.mkGroup([])) == 1
+
+
+def test_basis_argument_errors():
+    g = ffi.mkGroup([])
+    with pytest.raises(ffi.SpinEDException):
+        ffi.mkBasis(g, -2)
+    with pytest.raises(ffi.SpinEDException):
+        config.toBasis(config.BasisSpec(100, None, None, []))
+    with pytest.raises(ffi.LatticeSymmetriesException):
+        ffi.mkBasis(g, 4, 5)
+    with pytest.raises(ffi.LatticeSymmetriesException):
+        ffi.mkBasis(g, 4, 1, 1)
+    b = ffi.mkBasis(g, 4, 2)
+    with pytest.raises(ffi.LatticeSymmetriesException) as e:
+        ffi.getNumberStates(b)  # not built
+    assert e.value.eCode == 14
+
+
+def test_interaction_semantics():
+    # /root/reference/test/Spec.hs:96-104
+    t = ffi.mkInteraction([[1.0, 0.0], [0.0, -1.0]], [[0], [2]])
+    assert ffi.isRealInteraction(t)
+    t2 = ffi.mkInteraction([[0, [0, -1]], [[0, 1], 0]], [[0]])
+    assert not ffi.isRealInteraction(t2)
+    with pytest.raises(ffi.SpinEDException):
+        ffi.mkInteraction([[1, 2, 1], [4, 2, 1], [1, -2, 3]], [[0, 0, 0]])
+    with pytest.raises(ffi.SpinEDException):
+        ffi.mkInteraction([[1, 0], [0, 1]], [])
+
+
+def test_compute_fails_loudly_without_gpu():
+    try:
+        ffi.deviceCount()
+        pytest.skip("a CUDA device is present")
+    except ffi.LatticeSymmetriesException as e:
+        assert e.eCode == 100
+    uc = product_problem(decks.load("heisenberg_chain_10"))
+    with pytest.raises(ffi.LatticeSymmetriesException) as e:
+        ffi.buildBasis(uc.cBasis)
+    assert e.value.eCode == 100
+
+
+@pytest.mark.parametrize("name", SMALL_DECKS + ["heisenberg_square_5x5", "heisenberg_pyrochlore_32", "heisenberg_square_6x6",
+                                                "heisenberg_chain_40", "heisenberg_chain_42"])
+def test_program_matches_oracle_state_info(oracle, name):
+    """The compiled canonicalisation program (interpreted on the host) must give the oracle's
+    representative, character and norm for random states of the sector."""
+    cfg = decks.load(name)
+    ob, _ = oracle_problem(oracle, cfg)
+    if ob.group_size * (2 if ob.spin_inversion else 1) <= 1:
+        pytest.skip("trivial group")
+    uc = product_problem(cfg)
+    n, hw = ob.number_spins, ob.hamming_weight
+    rng = np.random.default_rng(1234)
+    states = []
+    for _ in range(300):
+        if hw is None:
+            states.append(int(rng.integers(0, 1 << n, dtype=np.uint64)))
+        else:
+            pos = rng.choice(n, size=hw, replace=False)
+            states.append(int(sum(1 << int(p) for p in pos)))
+    s = np.array(states, dtype=np.uint64)
+    reps = np.zeros(len(s), dtype=np.uint64)
+    phases = np.zeros(len(s), dtype=np.int32)
+    stabs = np.zeros(len(s), dtype=np.int32)
+    ffi.checkStatus(ffi.lib().sped_selftest_program(uc.cBasis._ptr, len(s), s.ctypes.data, reps.ctypes.data,
+                                                    phases.ctypes.data, stabs.ctypes.data))
+    order = ob.group_size * (2 if ob.spin_inversion else 1)
+    denom = np.lcm.reduce([2] + [oracle.periodicity(sym["permutation"]) for sym in cfg["basis"]["symmetries"]])
+    for x, r, ph, st in zip(states, reps, phases, stabs):
+        orep, ochi, onorm = ob.state_info(x)
+        assert int(r) == orep
+        assert abs(np.sqrt(st / order) - onorm) < 1e-15
+        if onorm > 0:
+            assert abs(np.exp(2j * np.pi * ph / denom) - ochi) < 1e-12
+
+
+@pytest.mark.parametrize("name", sorted(decks.names()))
+def test_burnside_dimension(oracle, name):
+    cfg = decks.load(name)
+    uc = product_problem(cfg)
+    out = C.c_uint64(0)
+    ffi.checkStatus(ffi.lib().sped_selftest_burnside(uc.cBasis._ptr, C.byref(out)))
+    known = {"heisenberg_chain_4": 16, "heisenberg_chain_10": 13, "heisenberg_kagome_12": 924, "heisenberg_square_4x4": 107,
+             "heisenberg_triangular_19": 4862, "xxz_triangular_19": 524288, "heisenberg_chain_24": 2704156,
+             "heisenberg_square_6x6": 15804956, "heisenberg_pyrochlore_32": 789438, "heisenberg_chain_40": 861725794,
+             "heisenberg_chain_42": 3204236779, "heisenberg_square_5x5": 208012}
+    assert out.value == known[name]
+
+
+@pytest.mark.parametrize("name", sorted(extra_configs()))
+def test_burnside_matches_oracle_on_corner_cases(oracle, name):
+    cfg = extra_configs()[name]
+    ob, _ = oracle_problem(oracle, cfg)
+    ob.build()
+    uc = product_problem(cfg)
+    out = C.c_uint64(0)
+    ffi.checkStatus(ffi.lib().sped_selftest_burnside(uc.cBasis._ptr, C.byref(out)))
+    assert out.value == ob.number_states
+
+
+def test_program_is_cheap_for_translation_groups():
+    uc = product_problem(decks.load("heisenberg_square_6x6"))
+    st = ffi.basisProgramStats(uc.cBasis)
+    assert st["steps"] == 288
+    # translations are two masked rotates; a generic Benes network would be ~11 swaps per element
+    assert st["rotate_mask_ops"] + st["delta_swap_ops"] < 4 * st["steps"]
+
+
+@pytest.mark.parametrize("m", [1, 2, 5, 17, 40])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_small_eigh_matches_numpy(m, cplx):
+    rng = np.random.default_rng(m)
+    A = rng.standard_normal((m, m)) + (1j * rng.standard_normal((m, m)) if cplx else 0)
+    A = (A + A.conj().T) / 2
+    a = np.ascontiguousarray(A.astype(np.complex128))
+    ev = np.zeros(m)
+    V = np.zeros((m, m), dtype=np.complex128)
+    ffi.checkStatus(ffi.lib().sped_selftest_small_eigh(m, a.ctypes.data, ev.ctypes.data, V.ctypes.data))
+    assert np.allclose(ev, np.linalg.eigvalsh(A), atol=1e-12)
+    assert np.allclose(A @ V, V * ev, atol=1e-11)
+    assert np.allclose(V.conj().T @ V, np.eye(m), atol=1e-12)
+
+
+def test_row_partition_covers_rows_in_equal_chunks():
+    for n in [0, 1, 7, 13, 1000, 861725794]:
+        for world in [1, 2, 3, 8]:
+            spans = [ffi.rowPartition(n, world, r) for r in range(world)]
+            chunk = -(-n // world) if n else 0
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for r in range(world):
+                assert spans[r][0] == min(n, r * chunk)
+                if r:
+                    assert spans[r][0] == spans[r - 1][1]
+
+
+def test_config_defaults_and_parsing():
+    # /root/reference/src/SpinED.hs:158-173
+    spec = config.parseConfig(decks.load("heisenberg_chain_4"))
+    assert spec.output == "exact_diagonalization_result.h5" and spec.number_vectors == 1
+    assert spec.precision == 0.0 and spec.datatype == "float64"
+    spec = config.parseConfig(decks.load("heisenberg_square_6x6"))
+    assert spec.datatype == "float32" and spec.max_primme_basis_size == 20 and spec.max_primme_block_size == 4
+    with pytest.raises(ffi.SpinEDException):
+        config.parseDatatype("complex64")
+    with pytest.raises(ffi.SpinEDException):
+        config.parseConfig({"basis": {"number_spins": 2, "symmetries": []}})
