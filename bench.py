@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- matvec matrix-elements/s of the symmetry-adapted Hamiltonian on B200 (+ basis-build
+time and time-to-ground-state), with the CPU restatement timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config DECK]
+
+A step is one application y = H x of the deck's Hamiltonian to one Krylov vector (block size 1):
+at N > 1 the step is what the solver does per matvec -- NCCL all-gather of the row-sharded vector
+followed by the kernel on the local row block.  `value` = (N_rows + E_offdiag) / t with inputs
+resident in HBM; `e2e` = the same through the reference-facing `ls_operator_matmat` with HOST
+buffers (H2D of x and D2H of y inside the timed region).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+DEFAULT_DECK = "heisenberg_square_6x6"
+METRIC = "matvec_matrix_elements_per_s"
+UNIT = "matrix-elements/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n_rows, n_off, elem_size, symmetric):
+    """B = N (8 rep + 8 diag + T y + 8 norm if symmetric) + E T."""
+    return n_rows * (8 + 8 + elem_size + (8 if symmetric else 0)) + n_off * elem_size
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index=0):
+        self.proc = None
+        self.device_index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample_rate(O, oop, n, seconds, dtype=np.float64):
+    """Time the oracle matvec on a strided row sample sized for about `seconds` of CPU work."""
+    from helpers import splitmix_vector
+
+    x = splitmix_vector(n, 0x5EED0001, dtype)
+    x /= np.linalg.norm(x)
+    y = np.zeros_like(x)
+    probe = min(n, 512 * O.num_threads())
+    stride = max(1, n // probe)
+    t0 = time.perf_counter()
+    e = oop.matmat_rows(x, y, 0, n, stride)
+    dt = time.perf_counter() - t0
+    rows = len(range(0, n, stride))
+    rate_rows = rows / max(dt, 1e-9)
+    target = int(max(rows, min(n, rate_rows * seconds)))
+    stride = max(1, n // target)
+    return x, y, stride
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement (oracle port) of the same path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from helpers import oracle_problem
+    from oracle import oracle as O
+    from spin_ed_b200 import decks
+
+    O.build()
+    cfg = decks.load(args.config)
+    ob, terms = oracle_problem(O, cfg)
+    cache = os.path.join("/tmp", f"sped_oracle_reps_{args.config}.npy")
+    t0 = time.perf_counter()
+    if os.path.exists(cache):
+        ob.build(np.load(cache))
+    else:
+        ob.build()
+        try:
+            np.save(cache, ob.states)
+        except Exception:
+            pass
+    build_s = time.perf_counter() - t0
+    oop = O.Operator(ob, terms)
+    n = ob.number_states
+    dtype = np.float64 if oop.is_real else np.complex128
+    x, y, stride = cpu_sample_rate(O, oop, n, args.cpu_seconds / 3.0, dtype)
+    rows = len(range(0, n, stride))
+    times, elems = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        e = oop.matmat_rows(x, y, 0, n, stride)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            elems = rows + e
+    t = sum(times) / len(times)
+    value = elems / t
+    sample = f"{rows} of {n} rows (every {stride}-th), {elems} matrix elements per step, float64, OpenMP"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.config, "rows": n, "note": "CPU restatement of the reference path (oracle port), not the "
+                   "upstream binary: lattice-symmetries/PRIMME are absent and cannot be built offline"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "extra": {"basis_build_s_cpu": build_s},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from helpers import splitmix_vector
+    from spin_ed_b200 import config as sconfig
+    from spin_ed_b200 import decks, ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    ffi.setDevice(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        box = [ffi.commUniqueId() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ffi.commInit(world, rank, box[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = decks.load(args.config)
+    spec = sconfig.parseConfig(cfg)
+    uc = sconfig.toConfig(spec)
+    basis, op = uc.cBasis, uc.cHamiltonian.operatorObject
+    barrier()
+    t0 = time.perf_counter()
+    ffi.buildBasis(basis)
+    barrier()
+    build_wall = time.perf_counter() - t0
+    n = ffi.getNumberStates(basis)
+    is_real = ffi.isOperatorReal(op)
+    np_dtype = np.float64 if is_real else np.complex128
+    t_dtype = torch.float64 if is_real else torch.complex128
+    tag = ffi.DTYPE_TAGS[np.dtype(np_dtype)]
+    es = np.dtype(np_dtype).itemsize
+    rows, n_off = ffi.operatorCountElements(op)
+    row0, row1 = ffi.basisLocalRows(basis)
+    n_local = row1 - row0
+    chunk = -(-n // world)
+    symmetric = ffi.basisProgramStats(basis)["steps"] > 1 or cfg["basis"].get("spin_inversion") is not None
+    log(f"[rank {rank}] {args.config}: N={n} E={n_off} local rows [{row0},{row1}) build {build_wall:.3f}s")
+
+    # device-resident inputs: the replicated vector (padded to world * chunk) and the local output
+    xh = splitmix_vector(n, 0x5EED0001, np_dtype)
+    xh /= np.linalg.norm(xh)
+    xfull = torch.zeros(chunk * world, dtype=t_dtype, device=dev)
+    xfull[:n].copy_(torch.from_numpy(xh))
+    xshard = xfull[rank * chunk:(rank + 1) * chunk].clone()
+    ylocal = torch.zeros(max(n_local, 1), dtype=t_dtype, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        if world > 1:
+            dist.all_gather_into_tensor(xfull, xshard)
+        ffi.operatorMatmatDevice(op, tag, 1, xfull.data_ptr(), chunk * world, ylocal.data_ptr(), max(n_local, 1),
+                                 stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ffi.kernelLaunches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = ffi.kernelLaunches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t_local = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    total_ms = float(t_local.item())
+    ms_per_step = total_ms / args.steps
+    value = (rows + n_off) / (ms_per_step * 1e-3)
+    # dominant kernel: the matvec kernel is the only kernel of ours in a step
+    kern_ms = ms_per_step if world == 1 else None
+    if world > 1:
+        # time the kernel alone (no all-gather) for the per-GPU roofline
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            ffi.operatorMatmatDevice(op, tag, 1, xfull.data_ptr(), chunk * world, ylocal.data_ptr(), max(n_local, 1),
+                                     stream.cuda_stream)
+        b.record()
+        barrier()
+        kern_ms = a.elapsed_time(b) / args.steps
+    peak, peak_src = measured_peak()
+    local_off = n_off * n_local / max(n, 1)
+    alg_bytes = algorithmic_bytes(n_local, local_off, es, symmetric)
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.config, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # end-to-end through the reference-facing C ABI with host buffers
+    y_host = torch.zeros(n, dtype=t_dtype).pin_memory().numpy()
+    x_host_t = torch.from_numpy(xh).pin_memory()
+    x_host = x_host_t.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ffi.inplaceApply(op, x_host, y_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ffi.inplaceApply(op, x_host, y_host)
+    barrier()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = (rows + n_off) / float(e2e_t.item())
+    # consistency of the two paths (same rows, same data)
+    dev_y = ylocal[:n_local].cpu().numpy()
+    if n_local and not np.allclose(dev_y, y_host[row0:row1], rtol=1e-12, atol=1e-14):
+        raise SystemExit("device-resident and host-pointer matvec disagree")
+
+    extra = {"basis_build_s": build_wall, "basis_build_device_s": ffi.basisBuildSeconds(basis), "rows": rows,
+             "offdiag_elements": n_off, "program": ffi.basisProgramStats(basis), "peak_source": peak_src,
+             "kernel_ms": kern_ms}
+    if not args.no_eigh:
+        barrier()
+        t0 = time.perf_counter()
+        evals, _, rnorms = ffi.eigh(op, np.dtype(np_dtype), spec.number_vectors, spec.precision, spec.max_primme_basis_size,
+                                    spec.max_primme_block_size, spec.min_primme_restart_size, want_vectors=False)
+        barrier()
+        st = ffi.eighLastStats(op)
+        extra.update({"time_to_ground_state_s": time.perf_counter() - t0, "eigenvalues": [float(v) for v in evals],
+                      "residual_norms": [float(v) for v in rnorms], "eigh_matvecs": st["matvecs"],
+                      "eigh_restarts": st["restarts"], "eigh_seconds_matvec": st["seconds_matvec"],
+                      "eigh_dtype": "f64 (deck asks " + spec.datatype + ")"})
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from helpers import oracle_problem
+        from oracle import oracle as O
+
+        O.build()
+        ob, terms = oracle_problem(O, cfg)
+        ob.build(np.array(ffi.basisGetStates(basis)))  # adopt the representatives (oracle computes its own norms)
+        oop = O.Operator(ob, terms)
+        xs, ys, stride = cpu_sample_rate(O, oop, n, args.cpu_seconds, np_dtype)
+        t0 = time.perf_counter()
+        e = oop.matmat_rows(xs, ys, 0, n, stride)
+        dt = time.perf_counter() - t0
+        srows = len(range(0, n, stride))
+        # the sampled rows must agree with the GPU result (full-size parity on the sample)
+        gpu_rows = y_host[0:n:stride]
+        err = np.linalg.norm(ys[0:n:stride] - gpu_rows) / max(np.linalg.norm(gpu_rows), 1e-300)
+        extra["sample_parity_rel_l2"] = float(err)
+        cpu_baseline = {"value": (srows + e) / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+                        "sample": f"{srows} of {n} rows (every {stride}-th), {srows + e} matrix elements, {dt:.1f} s; "
+                                  "oracle port (OpenMP), not the upstream binary"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if is_real else "c128", "data": "synthetic",
+            "config": {"workload": args.config, "rows": rows, "offdiag_elements": n_off, "block_size": 1,
+                       "parallelism": f"rows block-partitioned over {world} GPU(s), Krylov vector all-gathered (NCCL)",
+                       "l2": "inputs larger than L2 (no flush)" if alg_bytes > 126e6 else "inputs fit in L2 (no flush)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * es, "d2h_bytes_per_step": n * es},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes},
+            "cpu_baseline": cpu_baseline, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        ffi.commFinalize()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_DECK)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-eigh", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
+
+
+if __name__ == "__main__":
+    main()

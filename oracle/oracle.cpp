@@ -489,13 +489,18 @@ template <> struct Scalar<cplx> { static cplx load(const cplx* p) { return *p; }
 
 // y = H x (column-major blocks), optionally also counts matrix elements
 template <class T>
-int matmat(const Operator& op, u64 size, u64 block, const T* x, u64 xs, T* y, u64 ys, u64* n_offdiag) {
+int matmat(const Operator& op, u64 size, u64 block, const T* x, u64 xs, T* y, u64 ys, u64* n_offdiag,
+           u64 row_lo = 0, u64 row_hi = ~0ull, u64 row_stride = 1) {
   const Basis& B = *op.basis;
   if (!B.built) return ORC_NOT_BUILT;
   if (size != B.reps.size()) return ORC_DIMENSION_MISMATCH;
   u64 count = 0;
-#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : count)
-  for (i64 row = 0; row < (i64)size; ++row) {
+  if (row_hi > size) row_hi = size;
+  if (row_stride == 0) row_stride = 1;
+  const i64 n_rows = row_hi > row_lo ? (i64)((row_hi - row_lo + row_stride - 1) / row_stride) : 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : count)
+  for (i64 it = 0; it < n_rows; ++it) {
+    const i64 row = (i64)(row_lo + (u64)it * row_stride);
     const u64 r = B.reps[row];
     const double nr = B.norms[row];
     std::vector<cplx> acc(block, cplx(0, 0));
@@ -616,16 +621,22 @@ int orc_operator_add_term(void* op, int k, const double* matrix, int count, cons
 }
 int orc_operator_is_real(void* op) { return ((Operator*)op)->is_real() ? 1 : 0; }
 
-int orc_operator_matmat(void* op, int dtype, u64 size, u64 block, const void* x, u64 xs, void* y, u64 ys, u64* n_offdiag) {
+// rows row_lo, row_lo + stride, ... < row_hi only (bounded samples for CPU timing); y keeps the
+// full layout, untouched rows are left as they are.
+int orc_operator_matmat_rows(void* op, int dtype, u64 size, u64 block, const void* x, u64 xs, void* y, u64 ys,
+                             u64* n_offdiag, u64 row_lo, u64 row_hi, u64 row_stride) {
   Operator& o = *(Operator*)op;
   if ((dtype == 0 || dtype == 1) && !o.is_real()) return ORC_INVALID_DATATYPE;
   switch (dtype) {
-    case 0: return matmat<float>(o, size, block, (const float*)x, xs, (float*)y, ys, n_offdiag);
-    case 1: return matmat<double>(o, size, block, (const double*)x, xs, (double*)y, ys, n_offdiag);
-    case 2: return matmat<std::complex<float>>(o, size, block, (const std::complex<float>*)x, xs, (std::complex<float>*)y, ys, n_offdiag);
-    case 3: return matmat<cplx>(o, size, block, (const cplx*)x, xs, (cplx*)y, ys, n_offdiag);
+    case 0: return matmat<float>(o, size, block, (const float*)x, xs, (float*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
+    case 1: return matmat<double>(o, size, block, (const double*)x, xs, (double*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
+    case 2: return matmat<std::complex<float>>(o, size, block, (const std::complex<float>*)x, xs, (std::complex<float>*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
+    case 3: return matmat<cplx>(o, size, block, (const cplx*)x, xs, (cplx*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
   }
   return ORC_INVALID_DATATYPE;
+}
+int orc_operator_matmat(void* op, int dtype, u64 size, u64 block, const void* x, u64 xs, void* y, u64 ys, u64* n_offdiag) {
+  return orc_operator_matmat_rows(op, dtype, size, block, x, xs, y, ys, n_offdiag, 0, ~0ull, 1);
 }
 
 // out[k] = <x_k | O | x_k>  (complex128), via a c128 matvec

@@ -71,6 +71,7 @@ def lib():
         L.orc_operator_add_term.argtypes = [vp, ci, vp, ci, vp]
         L.orc_operator_is_real.argtypes = [vp]
         L.orc_operator_matmat.argtypes = [vp, ci, u64, u64, vp, u64, vp, u64, C.POINTER(u64)]
+        L.orc_operator_matmat_rows.argtypes = [vp, ci, u64, u64, vp, u64, vp, u64, C.POINTER(u64), u64, u64, u64]
         L.orc_operator_expectation.argtypes = [vp, ci, u64, u64, vp, u64, vp]
         L.orc_num_threads.restype = ci
         L.orc_set_num_threads.argtypes = [ci]
@@ -211,6 +212,14 @@ class Operator:
         )
         Y = Y[:, 0] if squeeze else Y
         return (Y, int(n_off.value)) if count else Y
+
+    def matmat_rows(self, x: np.ndarray, y: np.ndarray, row_lo: int, row_hi: int, row_stride: int = 1) -> int:
+        """Rows row_lo, row_lo+stride, ... < row_hi of y = H x (1-D x, y); returns the number of
+        off-diagonal elements visited.  Bounded-sample entry for CPU timing."""
+        n_off = C.c_uint64(0)
+        _check(lib().orc_operator_matmat_rows(self._h, DTYPES[x.dtype], len(x), 1, x.ctypes.data, len(x), y.ctypes.data,
+                                              len(y), C.byref(n_off), row_lo, row_hi, row_stride))
+        return int(n_off.value)
 
     def count_offdiag(self) -> int:
         """E = number of off-diagonal term applications with non-zero target norm."""

@@ -67,7 +67,7 @@ template <class W>
 __global__ void __launch_bounds__(kThreads) mark_kernel(EnumParams p, ProgramView<W> prog, bool staged, u64* marks,
                                                         u32* block_counts) {
   extern __shared__ __align__(16) unsigned char smem[];
-  ProgramView<W> P = stage_program<W>(prog, smem, staged);
+  ProgramView<W> P = stage_program<W>(prog, smem);
   u64 tid = (u64)blockIdx.x * kThreads + threadIdx.x;
   u64 r0 = p.rank_lo + tid * kCandPerThread;
   u64 mask = 0;
@@ -171,7 +171,7 @@ template <class W>
 __global__ void __launch_bounds__(kThreads) stabilizer_kernel(ProgramView<W> prog, bool staged, u64 const* reps,
                                                               u64 n, std::uint16_t* stab, int* invalid) {
   extern __shared__ __align__(16) unsigned char smem[];
-  ProgramView<W> P = stage_program<W>(prog, smem, staged);
+  ProgramView<W> P = stage_program<W>(prog, smem);
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     int s = stabilizer_scan<W>(P, (W)reps[i], true);
     if (s <= 0) {
@@ -199,7 +199,7 @@ template <class W>
 __global__ void __launch_bounds__(kThreads) state_info_kernel(ProgramView<W> prog, bool staged, u64 const* states,
                                                               u64 n, u64* reps, std::int32_t* phases, int* stabs) {
   extern __shared__ __align__(16) unsigned char smem[];
-  ProgramView<W> P = stage_program<W>(prog, smem, staged);
+  ProgramView<W> P = stage_program<W>(prog, smem);
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     W rep;
     u32 step, flipped;
@@ -231,32 +231,48 @@ struct DeviceProgram {
   bool staged;
 };
 
-constexpr size_t kMaxStagedProgram = 96 * 1024;
+constexpr size_t kMaxStagedProgram = 160 * 1024;
 
 }  // namespace
 
-// device image of the program: [steps][ops32][ops64][phase]
+// device image of the program: [steps][phase][ops32][ops64][fast32][fast64]
+namespace {
+struct ProgramLayout {
+  size_t steps, phase, ops32, ops64, fast32, fast64, total;
+};
+ProgramLayout program_layout(HostProgram const& P) {
+  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  ProgramLayout L;
+  L.steps = 0;
+  L.phase = L.steps + up(P.steps.size() * sizeof(PermStep));
+  L.ops32 = L.phase + up(P.phase.size() * sizeof(std::int32_t));
+  L.ops64 = L.ops32 + up(P.ops.size() * sizeof(PermOp<u32>));
+  L.fast32 = L.ops64 + up(P.ops.size() * sizeof(PermOp<u64>));
+  L.fast64 = L.fast32 + up(P.fast.size() * sizeof(FastStep<u32>));
+  L.total = L.fast64 + up(P.fast.size() * sizeof(FastStep<u64>));
+  return L;
+}
+}  // namespace
+
 template <class W>
 static DeviceProgram<W> device_program(Basis const& b) {
   DeviceProgram<W> d;
   auto const& P = b.program;
-  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  size_t off_steps = 0;
-  size_t off_ops32 = off_steps + up(P.steps.size() * sizeof(PermStep));
-  size_t off_ops64 = off_ops32 + up(P.ops.size() * sizeof(PermOp<u32>));
-  size_t off_phase = off_ops64 + up(P.ops.size() * sizeof(PermOp<u64>));
+  ProgramLayout L = program_layout(P);
   unsigned char* base = b.d_program.ptr;
-  d.view.steps = reinterpret_cast<PermStep const*>(base + off_steps);
-  d.view.ops = reinterpret_cast<PermOp<W> const*>(base + (sizeof(W) == 4 ? off_ops32 : off_ops64));
-  d.view.phase = reinterpret_cast<std::int32_t const*>(base + off_phase);
+  d.view.fast = reinterpret_cast<FastStep<W> const*>(base + (sizeof(W) == 4 ? L.fast32 : L.fast64));
+  d.view.steps = reinterpret_cast<PermStep const*>(base + L.steps);
+  d.view.ops = reinterpret_cast<PermOp<W> const*>(base + (sizeof(W) == 4 ? L.ops32 : L.ops64));
+  d.view.phase = reinterpret_cast<std::int32_t const*>(base + L.phase);
   d.view.n_steps = (u32)P.steps.size();
   d.view.n_ops = (u32)P.ops.size();
   d.view.n_spins = P.n_spins;
+  d.view.shift = sizeof(W) == 4 ? 0 : P.shift;
   d.view.inversion = P.inversion;
   d.view.denom = P.denom;
   d.smem = program_smem_bytes<W>(d.view.n_steps, d.view.n_ops);
-  d.staged = d.smem <= kMaxStagedProgram;
-  if (!d.staged) d.smem = 0;
+  if (d.smem > kMaxStagedProgram) fail(LS_INVALID_ARGUMENT, "symmetry group too large to stage its program in shared memory");
+  d.staged = true;
   return d;
 }
 template DeviceProgram<u32> device_program<u32>(Basis const&);
@@ -283,20 +299,20 @@ u64 Basis::expected_dimension() const {
 void Basis::ensure_device_tables() {
   if (d_norm_table.ptr) return;
   auto const& P = program;
-  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  ProgramLayout L = program_layout(P);
   std::vector<PermOp<u32>> ops32;
   for (auto const& o : P.ops) ops32.push_back(PermOp<u32>{(u32)o.mask, o.amount});
-  size_t off_ops32 = up(P.steps.size() * sizeof(PermStep));
-  size_t off_ops64 = off_ops32 + up(P.ops.size() * sizeof(PermOp<u32>));
-  size_t off_phase = off_ops64 + up(P.ops.size() * sizeof(PermOp<u64>));
-  size_t total = off_phase + up(P.phase.size() * sizeof(std::int32_t));
-  std::vector<unsigned char> img(total, 0);
-  std::memcpy(img.data(), P.steps.data(), P.steps.size() * sizeof(PermStep));
+  std::vector<FastStep<u32>> fast32;
+  for (auto const& f : P.fast) fast32.push_back(FastStep<u32>{(u32)f.mask, f.ctl});
+  std::vector<unsigned char> img(L.total, 0);
+  std::memcpy(img.data() + L.steps, P.steps.data(), P.steps.size() * sizeof(PermStep));
+  std::memcpy(img.data() + L.phase, P.phase.data(), P.phase.size() * sizeof(std::int32_t));
   if (!P.ops.empty()) {
-    std::memcpy(img.data() + off_ops32, ops32.data(), ops32.size() * sizeof(PermOp<u32>));
-    std::memcpy(img.data() + off_ops64, P.ops.data(), P.ops.size() * sizeof(PermOp<u64>));
+    std::memcpy(img.data() + L.ops32, ops32.data(), ops32.size() * sizeof(PermOp<u32>));
+    std::memcpy(img.data() + L.ops64, P.ops.data(), P.ops.size() * sizeof(PermOp<u64>));
   }
-  std::memcpy(img.data() + off_phase, P.phase.data(), P.phase.size() * sizeof(std::int32_t));
+  std::memcpy(img.data() + L.fast32, fast32.data(), fast32.size() * sizeof(FastStep<u32>));
+  std::memcpy(img.data() + L.fast64, P.fast.data(), P.fast.size() * sizeof(FastStep<u64>));
   d_program.upload(img);
   u64 order = group_order();
   std::vector<double> norms(order + 1);

@@ -269,7 +269,7 @@ int sped_basis_program_stats(void const* basis, unsigned* steps, unsigned* rot_o
   return guard([&] {
     auto& b = from_handle<Basis>(basis);
     *steps = (unsigned)b->program.steps.size();
-    *rot_ops = b->program.rot_ops;
+    *rot_ops = b->program.rot_ops + 2 * b->program.fast_steps;
     *benes_ops = b->program.benes_ops;
   });
 }
@@ -341,12 +341,14 @@ int sped_selftest_program(void const* basis, uint64_t count, uint64_t const* sta
   return guard([&] {
     auto& b = from_handle<Basis>(basis);
     auto const& P = b->program;
-    ProgramView<u64> v{P.steps.data(), P.ops.data(), P.phase.data(), (u32)P.steps.size(), (u32)P.ops.size(),
-                       P.n_spins, P.inversion, P.denom};
     std::vector<PermOp<u32>> ops32;
     for (auto const& o : P.ops) ops32.push_back(PermOp<u32>{(u32)o.mask, o.amount});
-    ProgramView<u32> v32{P.steps.data(), ops32.data(), P.phase.data(), (u32)P.steps.size(), (u32)P.ops.size(),
-                         P.n_spins, P.inversion, P.denom};
+    std::vector<FastStep<u32>> fast32;
+    for (auto const& f : P.fast) fast32.push_back(FastStep<u32>{(u32)f.mask, f.ctl});
+    ProgramView<u64> v{P.fast.data(), P.steps.data(), P.ops.data(), P.phase.data(), (u32)P.steps.size(),
+                       (u32)P.ops.size(), P.n_spins, P.shift, P.inversion, P.denom};
+    ProgramView<u32> v32{fast32.data(), P.steps.data(), ops32.data(), P.phase.data(), (u32)P.steps.size(),
+                         (u32)P.ops.size(), P.n_spins, 0, P.inversion, P.denom};
     for (u64 i = 0; i < count; ++i) {
       u32 step, flipped;
       if (b->use32()) {

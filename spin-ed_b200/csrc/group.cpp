@@ -204,23 +204,47 @@ std::vector<std::pair<u64, unsigned>> benes_stages(std::vector<int> src, unsigne
 }
 
 struct StepCode {
-  unsigned kind;
+  unsigned kind = 0;
   std::vector<PermOp<u64>> ops;
-  unsigned cost;
+  unsigned cost = 0;
+  bool fast = false;
+  FastStep<u64> fs{};
 };
 
-// Cheapest encoding of q (dest bit i <- source bit q[i]) on a W-bit word.
-StepCode encode_step(std::vector<int> const& q, unsigned n_spins, unsigned W) {
+// Cheapest encoding of q (spin i <- spin q[i]) on a W-bit word whose spins sit at bit positions
+// [shift, shift + n_spins).
+StepCode encode_step(std::vector<int> const& q, unsigned n_spins, unsigned W, unsigned shift) {
   std::map<unsigned, u64> classes;
-  for (unsigned i = 0; i < n_spins; ++i) classes[(i + W - (unsigned)q[i]) % W] |= 1ull << i;
-  unsigned per_rot = W == 32 ? 2 : 4, per_swap = W == 32 ? 6 : 11;
+  for (unsigned i = 0; i < n_spins; ++i) classes[(i + W - (unsigned)q[i]) % W] |= 1ull << (i + shift);
+  unsigned per_rot = W == 32 ? 2 : 4, per_swap = W == 32 ? 6 : 11, fast_cost = W == 32 ? 5 : 9;
   std::vector<int> src(W);
-  for (unsigned i = 0; i < W; ++i) src[i] = i < n_spins ? q[i] : (int)i;
+  for (unsigned i = 0; i < W; ++i) src[i] = (int)i;
+  for (unsigned i = 0; i < n_spins; ++i) src[i + shift] = q[i] + (int)shift;
   auto stages = benes_stages(src, W);
-  StepCode rot{0, {}, (unsigned)classes.size() * per_rot};
+  StepCode rot;
+  rot.kind = 0;
+  rot.cost = (unsigned)classes.size() * per_rot + 6;  // + general-step interpretation overhead
   for (auto const& c : classes) rot.ops.push_back(PermOp<u64>{c.second, c.first, 0});
-  if (stages.size() * per_swap < rot.cost) {
-    StepCode b{1, {}, (unsigned)stages.size() * per_swap};
+  if (classes.size() <= 2) {
+    rot.fast = true;
+    rot.cost = fast_cost;
+    auto it = classes.begin();
+    u64 all = (n_spins == 64 ? ~0ull : ((1ull << n_spins) - 1)) << shift;
+    unsigned r1 = it->first, r2 = it->first;
+    u64 m = all;
+    if (classes.size() == 2) {
+      m = it->second;
+      ++it;
+      r2 = it->first;
+    }
+    rot.fs.mask = m;
+    rot.fs.ctl = r1 | (r2 << 8);
+    return rot;
+  }
+  if (stages.size() * per_swap + 6 < rot.cost) {
+    StepCode b;
+    b.kind = 1;
+    b.cost = (unsigned)stages.size() * per_swap + 6;
     for (auto const& s : stages) b.ops.push_back(PermOp<u64>{s.first, s.second, 0});
     return b;
   }
@@ -241,12 +265,15 @@ HostProgram compile_program(Group const& g, unsigned n_spins, int inv) {
   P.inversion = inv;
   P.denom = (std::int32_t)g.denom;
   size_t const m = g.elems.size();
+  unsigned const W = n_spins <= 32 ? 32 : 64;
+  P.word_bits = W;
+  P.shift = (W == 64 && n_spins + kKeyShift <= 64 && 2 * m < (1u << kKeyShift)) ? kKeyShift : 0;
   P.steps.push_back(PermStep{0, 0, 0});
+  P.fast.push_back(FastStep<u64>{0, kFastGeneral, 0});
   P.phase.push_back(0);
   P.element.push_back(0);
   if (m <= 1) return P;
   if (g.n != n_spins) fail(LS_INVALID_ARGUMENT, "symmetry permutations must act on exactly number_spins sites");
-  unsigned const W = n_spins <= 32 ? 32 : 64;
 
   std::map<std::vector<int>, unsigned> where;
   for (size_t k = 0; k < m; ++k) where[g.elems[k].perm] = (unsigned)k;
@@ -255,7 +282,7 @@ HostProgram compile_program(Group const& g, unsigned n_spins, int inv) {
     for (unsigned i = 0; i < n_spins; ++i) inverse[k][g.elems[k].perm[i]] = (int)i;
   // cost of realising each group element as a single step
   std::vector<StepCode> code(m);
-  for (size_t k = 1; k < m; ++k) code[k] = encode_step(g.elems[k].perm, n_spins, W);
+  for (size_t k = 1; k < m; ++k) code[k] = encode_step(g.elems[k].perm, n_spins, W, P.shift);
 
   // greedy nearest-neighbour path through the group: from image g.x the image h.x is reached by
   // q = g^{-1} h  (q[i] = g^{-1}[h[i]]), itself a group element.
@@ -278,36 +305,47 @@ HostProgram compile_program(Group const& g, unsigned n_spins, int inv) {
       }
     }
     StepCode const& sc = code[best_q];
-    P.steps.push_back(PermStep{(std::uint32_t)P.ops.size(), (std::uint16_t)sc.ops.size(), (std::uint16_t)sc.kind});
-    for (auto const& o : sc.ops) P.ops.push_back(o);
-    (sc.kind == 0 ? P.rot_ops : P.benes_ops) += (std::uint32_t)sc.ops.size();
+    if (sc.fast) {
+      P.steps.push_back(PermStep{(std::uint32_t)P.ops.size(), 0, 0});
+      P.fast.push_back(sc.fs);
+      ++P.fast_steps;
+    } else {
+      P.steps.push_back(PermStep{(std::uint32_t)P.ops.size(), (std::uint16_t)sc.ops.size(), (std::uint16_t)sc.kind});
+      for (auto const& o : sc.ops) P.ops.push_back(o);
+      (sc.kind == 0 ? P.rot_ops : P.benes_ops) += (std::uint32_t)sc.ops.size();
+      P.fast.push_back(FastStep<u64>{0, kFastGeneral, 0});
+    }
     P.phase.push_back((std::int32_t)g.elems[best_h].phase);
     P.element.push_back(best_h);
     visited[best_h] = 1;
     cur = best_h;
   }
 
-  // verify the program against bit-by-bit application of every group element (both word widths
-  // share the 64-bit host ops; amounts were computed for W, so emulate W-bit rotation here)
+  // verify the program against bit-by-bit application of every group element
+  std::vector<PermOp<std::uint32_t>> ops32;
+  std::vector<FastStep<std::uint32_t>> fast32;
+  for (auto const& o : P.ops) ops32.push_back(PermOp<std::uint32_t>{(std::uint32_t)o.mask, o.amount});
+  for (auto const& f : P.fast) fast32.push_back(FastStep<std::uint32_t>{(std::uint32_t)f.mask, f.ctl});
+  ProgramView<u64> v64{P.fast.data(), P.steps.data(), P.ops.data(), P.phase.data(), (u32)P.steps.size(),
+                       (u32)P.ops.size(), n_spins, P.shift, inv, P.denom};
+  ProgramView<std::uint32_t> v32{fast32.data(), P.steps.data(), ops32.data(), P.phase.data(), (u32)P.steps.size(),
+                                 (u32)P.ops.size(), n_spins, 0, inv, P.denom};
   std::mt19937_64 rng(0x5EED5EEDull);
   u64 const all = n_spins == 64 ? ~0ull : ((1ull << n_spins) - 1);
   for (int trial = 0; trial < 16; ++trial) {
     u64 x = rng() & all;
-    u64 y = x;
+    u64 y64 = x << P.shift;
+    std::uint32_t y32 = (std::uint32_t)x;
     for (size_t k = 1; k < P.steps.size(); ++k) {
+      u64 got;
       if (W == 64) {
-        y = apply_step<u64>(y, P.steps[k], P.ops.data());
+        y64 = advance<u64>(v64, (u32)k, y64, full_mask<u64>(n_spins, P.shift));
+        got = y64 >> P.shift;
       } else {
-        std::vector<PermOp<std::uint32_t>> ops32;
-        for (unsigned j = 0; j < P.steps[k].n_ops; ++j) {
-          auto const& o = P.ops[P.steps[k].first_op + j];
-          ops32.push_back(PermOp<std::uint32_t>{(std::uint32_t)o.mask, o.amount});
-        }
-        PermStep st = P.steps[k];
-        st.first_op = 0;
-        y = apply_step<std::uint32_t>((std::uint32_t)y, st, ops32.data());
+        y32 = advance<std::uint32_t>(v32, (u32)k, y32, full_mask<std::uint32_t>(n_spins, 0));
+        got = y32;
       }
-      if (y != permute_naive(g.elems[P.element[k]].perm, x))
+      if (got != permute_naive(g.elems[P.element[k]].perm, x))
         fail(SPED_INTERNAL_ERROR, "canonicalisation program failed self-verification");
     }
   }

@@ -206,6 +206,7 @@ struct Operator {
   u64 prepared_generation = ~0ull;
   DeviceBuffer<unsigned char> d_terms;  // packed bonds + matrices (see operator.cu)
   DeviceBuffer<double> d_diag;          // local rows (real part) [+ imaginary part if !real_diagonal]
+  DeviceBuffer<unsigned char> stage_x, stage_y;  // grow-only device staging of the host-pointer entry
   u64 row_begin = 0, row_end = 0;
   bool counted = false;
   u64 n_offdiag = 0;

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) matvec_kernel(MatvecParams p, Progra
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<CPLX>(p.terms, smem);
   ProgramView<W> P = prog;
-  if (SYM) P = stage_program<W>(prog, smem + terms_smem_bytes(p.terms, CPLX), staged);
+  if (SYM) P = stage_program<W>(prog, smem + terms_smem_bytes(p.terms, CPLX));
   BasisIndex const ix = p.ctx.index;
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) count_kernel(MatvecParams p, Program
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(p.terms, smem);
   ProgramView<W> P = prog;
-  if (SYM) P = stage_program<W>(prog, smem + terms_smem_bytes(p.terms, false), staged);
+  if (SYM) P = stage_program<W>(prog, smem + terms_smem_bytes(p.terms, false));
   BasisIndex const ix = p.ctx.index;
   u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
   unsigned long long mine = 0;
@@ -607,7 +607,10 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   Comm& cm = comm();
   u64 chunk = (size + cm.world - 1) / cm.world;
   u64 padded = chunk * cm.world;
-  DeviceBuffer<unsigned char> dx(size * block * es), dy(padded * block * es);
+  // staging buffers are kept between calls (PRIMME calls this once per block per iteration)
+  if (stage_x.count < size * block * es) stage_x.alloc(size * block * es);
+  if (stage_y.count < padded * block * es) stage_y.alloc(padded * block * es);
+  DeviceBuffer<unsigned char>&dx = stage_x, &dy = stage_y;
   CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
   u64 n_local = row_end - row_begin;
   // y columns are laid out with stride `padded`; column c of the local block sits at chunk*rank
