@@ -16,6 +16,12 @@ int sped_selftest_program(void const* basis, uint64_t count, uint64_t const* sta
                           int* stabs);
 /* sector dimension by character-weighted Burnside counting */
 int sped_selftest_burnside(void const* basis, uint64_t* out);
+/* CUDA C++ source of the run-time specialised canonicalisation of this basis' symmetry group
+ * (what jit.cpp hands to NVRTC); writes at most `capacity` bytes, returns the full length. */
+int sped_selftest_jit_source(void const* basis, char* out, uint64_t capacity, uint64_t* needed);
+/* Compiles the specialised matvec kernel with NVRTC for sm_100a without loading it (no GPU
+ * needed); returns the cubin size. */
+int sped_selftest_jit_compile(void const* basis, int dtype, int columns, uint64_t* cubin_bytes);
 #ifdef __cplusplus
 }
 #endif

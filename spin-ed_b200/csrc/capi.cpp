@@ -4,6 +4,7 @@
 // /root/reference/src/SpinED/Internal.hs (line numbers in include/sped.h).  Handles are heap cells
 // holding a std::shared_ptr, so every object keeps what it depends on alive and the GHC finalizers
 // (Internal.hs:116,150,228,362,402) may run in any order.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -50,6 +51,8 @@ int guarded(void (*thunk)(void*), void* ctx) {
 
 void basis_state_info(Basis& b, u64 count, u64 const* states, u64* reps, double* chars, double* norms);
 void small_eigh(int m, std::vector<cplx> A, std::vector<double>& evals, std::vector<cplx>& evecs);
+std::string jit_program_source(Basis const& b);
+size_t jit_compile_only(Basis& b, int dtype, int nb);
 
 namespace {
 
@@ -369,6 +372,20 @@ int sped_selftest_program(void const* basis, uint64_t count, uint64_t const* sta
 }
 int sped_selftest_burnside(void const* basis, uint64_t* out) {
   return guard([&] { *out = from_handle<Basis>(basis)->expected_dimension(); });
+}
+int sped_selftest_jit_source(void const* basis, char* out, uint64_t capacity, uint64_t* needed) {
+  return guard([&] {
+    std::string src = jit_program_source(*from_handle<Basis>(basis));
+    *needed = src.size() + 1;
+    if (out && capacity) {
+      size_t n = std::min<size_t>(capacity - 1, src.size());
+      std::memcpy(out, src.data(), n);
+      out[n] = 0;
+    }
+  });
+}
+int sped_selftest_jit_compile(void const* basis, int dtype, int columns, uint64_t* cubin_bytes) {
+  return guard([&] { *cubin_bytes = jit_compile_only(*from_handle<Basis>(basis), dtype, columns); });
 }
 
 }  // extern "C"

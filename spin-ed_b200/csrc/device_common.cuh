@@ -1,4 +1,4 @@
-// device_common.cuh -- helpers shared by the sm_100a kernels.
+// device_common.cuh -- helpers shared by the statically compiled sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -49,35 +49,6 @@ __device__ __forceinline__ ProgramView<W> stage_program(ProgramView<W> g, unsign
   v.ops = ops;
   v.phase = phase;
   return v;
-}
-
-// Index of representative `rep` in the sorted array, or ~0 if absent.
-__device__ __forceinline__ u64 lookup_index(BasisIndex const& ix, u64 rep) {
-  if (ix.direct) return rep;
-  u64 prefix = rep >> ix.bucket_shift;
-  if (prefix >= ix.bucket_count) return ~0ull;
-  u64 lo, hi;
-  if (ix.bucket_wide) {
-    u64 const* b = static_cast<u64 const*>(ix.bucket);
-    lo = __ldg(b + prefix);
-    hi = __ldg(b + prefix + 1);
-  } else {
-    u32 const* b = static_cast<u32 const*>(ix.bucket);
-    lo = __ldg(b + prefix);
-    hi = __ldg(b + prefix + 1);
-  }
-  // branch-light binary search for the first element >= rep in [lo, hi)
-  while (lo < hi) {
-    u64 mid = lo + ((hi - lo) >> 1);
-    u64 v = __ldg(ix.reps + mid);
-    if (v < rep) lo = mid + 1;
-    else hi = mid;
-  }
-  if (lo < ix.n_states && __ldg(ix.reps + lo) == rep) {
-    // lo may have run to the end of the bucket; equality settles membership
-    return lo;
-  }
-  return ~0ull;
 }
 #endif
 

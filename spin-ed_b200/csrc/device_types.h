@@ -1,0 +1,67 @@
+// device_types.h -- plain-old-data records shared by the host code, the statically compiled
+// kernels and the run-time specialised (NVRTC) kernels.  Builtin types only: this header is also
+// compiled by NVRTC, which has no standard library headers.
+#pragma once
+
+namespace sped {
+
+#if defined(SPED_JIT)
+typedef unsigned long u64;   // LP64, same as std::uint64_t on the host side
+typedef long i64;
+typedef unsigned int u32;
+#endif
+typedef unsigned short dev_u16;
+typedef unsigned char dev_u8;
+typedef int dev_i32;
+
+// Lookup structures of a built basis (device pointers).
+struct BasisIndex {
+  u64 const* reps;        // sorted representatives, global, replicated on every rank
+  dev_u16 const* stab;    // |Stab| per representative (norm^2 = stab / |G'|); null for the trivial group
+  void const* bucket;     // prefix table: u32 or u64 entries
+  u64 n_states;
+  int bucket_shift;       // prefix = rep >> bucket_shift
+  u32 bucket_count;       // number of prefixes (table has bucket_count + 1 entries)
+  int bucket_wide;        // 1: u64 entries
+  int direct;             // 1: index == state (no hamming weight, trivial group)
+};
+
+// One term instance ("bond"): a k-site tuple and where its matrix lives in the pools.
+struct DevBond {
+  u32 sites;       // site j in bits [8j, 8j+8)
+  dev_u16 moff;    // offset (in matrix elements) of this bond's matrix in the pool
+  dev_u16 zoff;    // offset of its row masks in the mask pool
+  u32 k;           // number of sites (1..4)
+  u32 pad_;
+};
+
+struct TermsView {
+  DevBond const* bonds;
+  double const* pool_re;   // real parts of all matrices, row-major dim x dim each
+  double const* pool_im;   // imaginary parts (same layout)
+  dev_u16 const* masks;    // per matrix row a: bitmask of b != a with M[a][b] != 0
+  u32 n_bonds;
+  u32 pool_size;
+  u32 mask_size;
+};
+
+struct RowContext {
+  BasisIndex index;
+  double const* norm_table;  // norm_table[s] = sqrt(s / |G'|)
+  double const* chi_table;   // (cos, sin)(2 pi k / denom)
+  u64 row_begin, row_end;    // local rows (global indices)
+};
+
+struct MatvecParams {
+  RowContext ctx;
+  TermsView terms;
+  double const* diag_re;  // local rows
+  double const* diag_im;  // null when the diagonal is real
+  void const* x;          // replicated, column-major, stride xs
+  void* y;                // local rows, column-major, stride ys
+  u64 xs, ys;
+  u32 ncols;              // columns handled by this launch (<= NB)
+  unsigned long long* counter;  // count mode only
+};
+
+}  // namespace sped

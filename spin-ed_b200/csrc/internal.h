@@ -14,11 +14,15 @@
 #include "permprog.h"
 
 namespace sped {
-
 using u64 = std::uint64_t;
 using i64 = std::int64_t;
 using u32 = std::uint32_t;
 using cplx = std::complex<double>;
+}  // namespace sped
+
+#include "device_types.h"
+
+namespace sped {
 
 extern bool g_logging;
 extern std::uint64_t g_launches;
@@ -135,17 +139,6 @@ void comm_group_end();
 void row_partition(u64 n, int world, int rank, u64& begin, u64& end);
 
 // ---- basis (basis.cu) ----
-struct BasisIndex {  // device lookup structures, shared by kernels
-  u64 const* reps = nullptr;         // sorted representatives, global, replicated on every rank
-  std::uint16_t const* stab = nullptr;  // |Stab| per representative (norm^2 = stab / |G'|)
-  void const* bucket = nullptr;      // prefix table: u32 or u64 entries
-  u64 n_states = 0;
-  int bucket_shift = 0;              // prefix = rep >> bucket_shift
-  u32 bucket_count = 0;              // number of prefixes (table has bucket_count + 1 entries)
-  int bucket_wide = 0;               // 1: u64 entries
-  int direct = 0;                    // 1: index == state (no hamming weight, trivial group)
-};
-
 struct Basis {
   std::shared_ptr<Group> group;
   unsigned n_spins = 0;
@@ -165,6 +158,7 @@ struct Basis {
   BasisIndex index;
   double build_seconds = 0.0;
   std::shared_ptr<std::vector<u64>> host_reps;  // lazily mirrored for ls_get_states
+  std::shared_ptr<void> jit_cache;              // run-time specialised kernels (jit.cpp)
   u64 generation = 0;                           // bumped by every (re)build
 
   bool trivial() const { return group->elems.size() <= 1 && spin_inversion == 0; }

@@ -1,0 +1,332 @@
+// jit.cpp -- run-time specialisation of the matvec kernel on the symmetry group.
+//
+// The group program of a basis (permprog.h) is emitted as straight-line CUDA C++ -- every masked
+// rotate becomes funnel shifts and LOP3s with immediate operands, no loop, no loads -- and
+// compiled for sm_100a with NVRTC together with matvec_kernel.cuh (the very same device code the
+// static kernels use).  The resulting cubin is loaded with cudaLibraryLoadData and launched with
+// cudaLaunchKernel.  NVRTC is bound with dlopen; when it is missing, or SPED_JIT=0, the statically
+// compiled kernel with the interpreted program runs instead (same algorithm, ~2x the instructions).
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <cstdlib>
+#include <map>
+#include <sstream>
+
+#include "internal.h"
+
+namespace sped {
+
+extern char const k_src_device_types[];
+extern char const k_src_matvec_kernel[];
+
+namespace {
+
+struct NvrtcApi {
+  void* handle = nullptr;
+  bool tried = false;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+};
+
+NvrtcApi& nvrtc() {
+  static NvrtcApi a;
+  if (a.tried) return a;
+  a.tried = true;
+  char const* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                         "/usr/local/cuda/lib64/libnvrtc.so"};
+  for (char const* n : names) {
+    a.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (a.handle) break;
+  }
+  if (!a.handle) return a;
+  bool ok = true;
+  auto load = [&](char const* sym) {
+    void* p = dlsym(a.handle, sym);
+    if (!p) ok = false;
+    return p;
+  };
+  a.CreateProgram = reinterpret_cast<decltype(a.CreateProgram)>(load("nvrtcCreateProgram"));
+  a.CompileProgram = reinterpret_cast<decltype(a.CompileProgram)>(load("nvrtcCompileProgram"));
+  a.GetCUBINSize = reinterpret_cast<decltype(a.GetCUBINSize)>(load("nvrtcGetCUBINSize"));
+  a.GetCUBIN = reinterpret_cast<decltype(a.GetCUBIN)>(load("nvrtcGetCUBIN"));
+  a.GetProgramLogSize = reinterpret_cast<decltype(a.GetProgramLogSize)>(load("nvrtcGetProgramLogSize"));
+  a.GetProgramLog = reinterpret_cast<decltype(a.GetProgramLog)>(load("nvrtcGetProgramLog"));
+  a.DestroyProgram = reinterpret_cast<decltype(a.DestroyProgram)>(load("nvrtcDestroyProgram"));
+  if (!ok) a.handle = nullptr;
+  return a;
+}
+
+std::string hex32(u32 v) {
+  char buf[16];
+  std::snprintf(buf, sizeof buf, "0x%08xu", v);
+  return buf;
+}
+
+// ---- code generation -------------------------------------------------------------------------
+// 64-bit images are kept as (lo, hi) 32-bit halves so that rotates are explicit funnel shifts.
+struct Gen {
+  HostProgram const& P;
+  std::ostringstream o;
+  bool w32;
+  unsigned shift, top;
+  u64 all;
+
+  explicit Gen(HostProgram const& p) : P(p) {
+    w32 = P.word_bits == 32;
+    shift = w32 ? 0 : P.shift;
+    top = P.n_spins - 1 + shift;
+    all = (P.n_spins == 64 ? ~0ull : ((1ull << P.n_spins) - 1)) << shift;
+  }
+
+  // expression for half `h` (0 = lo, 1 = hi) of rotl64((lo,hi), r)
+  static std::string rot64(unsigned r, int h) {
+    r &= 63u;
+    if (r == 0) return h ? "hi" : "lo";
+    if (r == 32) return h ? "lo" : "hi";
+    char const* A = r < 32 ? "lo" : "hi";  // the pair being shifted is (A = low, B = high)
+    char const* B = r < 32 ? "hi" : "lo";
+    unsigned s = r & 31u;
+    std::ostringstream e;
+    if (h) e << "__funnelshift_l(" << A << ", " << B << ", " << s << ")";
+    else e << "__funnelshift_l(" << B << ", " << A << ", " << s << ")";
+    return e.str();
+  }
+  static std::string rot32(unsigned r) {
+    r &= 31u;
+    if (r == 0) return "lo";
+    std::ostringstream e;
+    e << "__funnelshift_l(lo, lo, " << r << ")";
+    return e.str();
+  }
+
+  // y <- OR_j (rotl(y, r_j) & m_j)
+  void emit_rotmask(std::vector<std::pair<unsigned, u64>> const& terms) {
+    o << "  {\n";
+    std::string lo_expr, hi_expr;
+    for (size_t j = 0; j < terms.size(); ++j) {
+      u32 mlo = (u32)terms[j].second, mhi = (u32)(terms[j].second >> 32);
+      if (w32) {
+        if (mlo) lo_expr += (lo_expr.empty() ? "" : " | ") + ("(" + rot32(terms[j].first) + " & " + hex32(mlo) + ")");
+      } else {
+        if (mlo) lo_expr += (lo_expr.empty() ? "" : " | ") + ("(" + rot64(terms[j].first, 0) + " & " + hex32(mlo) + ")");
+        if (mhi) hi_expr += (hi_expr.empty() ? "" : " | ") + ("(" + rot64(terms[j].first, 1) + " & " + hex32(mhi) + ")");
+      }
+    }
+    o << "    u32 nlo = " << (lo_expr.empty() ? "0u" : lo_expr) << ";\n";
+    if (!w32) o << "    u32 nhi = " << (hi_expr.empty() ? "0u" : hi_expr) << ";\n    hi = nhi;\n";
+    o << "    lo = nlo;\n  }\n";
+  }
+
+  void emit_benes(std::vector<std::pair<unsigned, u64>> const& swaps) {
+    if (w32) {
+      for (auto const& s : swaps)
+        o << "  { u32 t = ((lo >> " << s.first << ") ^ lo) & " << hex32((u32)s.second) << "; lo ^= t ^ (t << " << s.first
+          << "); }\n";
+    } else {
+      for (auto const& s : swaps)
+        o << "  { u64 y = ((u64)hi << 32) | lo; u64 t = ((y >> " << s.first << ") ^ y) & 0x" << std::hex << s.second
+          << std::dec << "ull; y ^= t ^ (t << " << s.first << "); lo = (u32)y; hi = (u32)(y >> 32); }\n";
+    }
+  }
+
+  // fold the spin inversion into (zlo, zhi, f), form the key and update the running minimum
+  void emit_visit(unsigned k) {
+    bool inv = P.inversion != 0;
+    o << "  {\n";
+    if (inv) {
+      if (w32 || top < 32) o << "    u32 f = (lo >> " << top << ") & 1u;\n";
+      else o << "    u32 f = (hi >> " << (top - 32) << ") & 1u;\n";
+      o << "    u32 m = 0u - f;\n";
+      o << "    u32 zlo = lo ^ (" << hex32((u32)all) << " & m);\n";
+      if (!w32) o << "    u32 zhi = hi ^ (" << hex32((u32)(all >> 32)) << " & m);\n";
+    } else {
+      o << "    u32 zlo = lo;\n";
+      if (!w32) o << "    u32 zhi = hi;\n";
+    }
+    std::string tag = std::to_string(2 * k) + "u" + (inv ? " + f" : "");
+    if (w32) {
+      o << "    u64 key = ((u64)zlo << 32) | (u64)(" << tag << ");\n";
+      o << "    best = key < best ? key : best;\n";
+    } else if (shift) {
+      o << "    u64 key = ((u64)zhi << 32) | (u64)(zlo | (" << tag << "));\n";
+      o << "    best = key < best ? key : best;\n";
+    } else {
+      o << "    u64 z = ((u64)zhi << 32) | zlo;\n";
+      o << "    if (z < best) { best = z; bidx = " << tag << "; }\n";
+    }
+    o << "  }\n";
+  }
+
+  std::string run() {
+    o << "namespace sped {\n";
+    o << "__device__ const int sped_jit_phase[" << P.phase.size() << "] = {";
+    for (size_t i = 0; i < P.phase.size(); ++i) o << (i ? "," : "") << P.phase[i];
+    o << "};\n";
+    o << "__device__ __forceinline__ void sped_jit_canonicalize(u64 x, u64& rep, int& phase) {\n";
+    if (w32) o << "  u32 lo = (u32)x;\n";
+    else o << "  u64 xs = x << " << shift << ";\n  u32 lo = (u32)xs, hi = (u32)(xs >> 32);\n";
+    o << "  u64 best = ~(u64)0;\n";
+    if (!w32 && !shift) o << "  u32 bidx = 0;\n";
+    emit_visit(0);
+    for (size_t k = 1; k < P.steps.size(); ++k) {
+      auto const& f = P.fast[k];
+      if (!(f.ctl & kFastGeneral)) {
+        unsigned r1 = f.ctl & 63u, r2 = (f.ctl >> 8) & 63u;
+        std::vector<std::pair<unsigned, u64>> t;
+        if (r1 == r2) t.push_back({r1, all});
+        else {
+          t.push_back({r1, f.mask & all});
+          t.push_back({r2, ~f.mask & all});
+        }
+        emit_rotmask(t);
+      } else {
+        auto const& st = P.steps[k];
+        std::vector<std::pair<unsigned, u64>> t;
+        for (unsigned j = 0; j < st.n_ops; ++j) t.push_back({P.ops[st.first_op + j].amount, P.ops[st.first_op + j].mask});
+        if (st.kind == 0) emit_rotmask(t);
+        else emit_benes(t);
+      }
+      emit_visit((unsigned)k);
+    }
+    if (w32) {
+      o << "  rep = (u64)(u32)(best >> 32);\n  u32 idx = (u32)best;\n";
+    } else if (shift) {
+      o << "  rep = best >> " << shift << ";\n  u32 idx = (u32)best & " << ((1u << shift) - 1u) << "u;\n";
+    } else {
+      o << "  rep = best;\n  u32 idx = bidx;\n";
+    }
+    o << "  int ph = sped_jit_phase[idx >> 1];\n";
+    if (P.inversion < 0) o << "  if (idx & 1u) { ph += " << P.denom / 2 << "; if (ph >= " << P.denom << ") ph -= " << P.denom << "; }\n";
+    o << "  phase = ph;\n}\n}  // namespace sped\n";
+    return o.str();
+  }
+};
+
+struct Entry {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kernel = nullptr;
+  bool failed = false;
+};
+
+struct Cache {
+  std::map<std::pair<int, int>, Entry> entries;
+  ~Cache() {
+    for (auto& e : entries)
+      if (e.second.lib) cudaLibraryUnload(e.second.lib);
+  }
+};
+
+std::mutex g_jit_mutex;
+
+char const* dtype_name(int dtype) {
+  switch (dtype) {
+    case SPED_F32: return "float";
+    case SPED_F64: return "double";
+    case SPED_C64: return "float2";
+    default: return "double2";
+  }
+}
+
+bool jit_enabled() {
+  char const* e = std::getenv("SPED_JIT");
+  return !(e && e[0] == '0');
+}
+
+// NVRTC: generated program + matvec_kernel.cuh -> sm_100a cubin (empty on failure)
+std::vector<char> compile_cubin(Basis& b, int dtype, int nb) {
+  std::vector<char> cubin;
+  NvrtcApi& api = nvrtc();
+  if (!api.handle) {
+    SPED_LOG("jit: NVRTC not available, using the interpreted-program kernel");
+    return cubin;
+  }
+  std::string program = Gen(b.program).run();
+  std::string header = std::string("#define SPED_T ") + dtype_name(dtype) + "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
+  std::string main_src =
+      "#define SPED_JIT 1\n#include \"device_types.h\"\n#include \"sped_jit_program.h\"\n#include \"matvec_kernel.cuh\"\n";
+  char const* hdr_src[] = {k_src_device_types, header.c_str(), k_src_matvec_kernel};
+  char const* hdr_names[] = {"device_types.h", "sped_jit_program.h", "matvec_kernel.cuh"};
+  nvrtcProgram prog = nullptr;
+  if (api.CreateProgram(&prog, main_src.c_str(), "sped_matvec_jit.cu", 3, hdr_src, hdr_names) != NVRTC_SUCCESS) return cubin;
+  char const* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  nvrtcResult rc = api.CompileProgram(prog, 4, opts);
+  if (rc != NVRTC_SUCCESS || g_logging) {
+    size_t n = 0;
+    api.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) api.GetProgramLog(prog, &log[0]);
+    if (rc != NVRTC_SUCCESS) {
+      std::fprintf(stderr, "[sped] jit: NVRTC compilation failed, using the interpreted-program kernel\n%s\n", log.c_str());
+      api.DestroyProgram(&prog);
+      return cubin;
+    }
+  }
+  size_t size = 0;
+  api.GetCUBINSize(prog, &size);
+  cubin.resize(size);
+  api.GetCUBIN(prog, cubin.data());
+  api.DestroyProgram(&prog);
+  if (char const* dump = std::getenv("SPED_JIT_DUMP")) {  // inspection: cuobjdump -sass <file>
+    if (FILE* f = std::fopen(dump, "wb")) {
+      std::fwrite(cubin.data(), 1, cubin.size(), f);
+      std::fclose(f);
+    }
+  }
+  return cubin;
+}
+
+Entry compile(Basis& b, int dtype, int nb) {
+  Entry out;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<char> cubin = compile_cubin(b, dtype, nb);
+  size_t size = cubin.size();
+  if (cubin.empty()) {
+    out.failed = true;
+    return out;
+  }
+  cudaError_t e = cudaLibraryLoadData(&out.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.kernel, out.lib, "sped_matvec_jit");
+  if (e != cudaSuccess) {
+    std::fprintf(stderr, "[sped] jit: loading the specialised kernel failed (%s), using the interpreted-program kernel\n",
+                 cudaGetErrorString(e));
+    cudaGetLastError();
+    out.failed = true;
+    out.kernel = nullptr;
+    return out;
+  }
+  double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  SPED_LOG("jit: specialised matvec (%s, %d columns, %zu steps) compiled in %.2f s, cubin %zu bytes", dtype_name(dtype), nb,
+           b.program.steps.size(), dt, size);
+  return out;
+}
+
+}  // namespace
+
+size_t jit_compile_only(Basis& b, int dtype, int nb) {
+  std::vector<char> cubin = compile_cubin(b, dtype, nb);
+  if (cubin.empty()) fail(SPED_INTERNAL_ERROR, "NVRTC compilation of the specialised kernel failed");
+  return cubin.size();
+}
+
+// Source of the specialised canonicalisation (exposed for tests and inspection).
+std::string jit_program_source(Basis const& b) { return Gen(b.program).run(); }
+
+void* jit_matvec_kernel(Basis& b, int dtype, int nb) {
+  if (!jit_enabled() || b.trivial()) return nullptr;
+  std::lock_guard<std::mutex> lock(g_jit_mutex);
+  if (!b.jit_cache) b.jit_cache = std::make_shared<Cache>();
+  Cache& c = *static_cast<Cache*>(b.jit_cache.get());
+  auto key = std::make_pair(dtype, nb);
+  auto it = c.entries.find(key);
+  if (it == c.entries.end()) it = c.entries.emplace(key, compile(b, dtype, nb)).first;
+  return it->second.failed ? nullptr : (void*)it->second.kernel;
+}
+
+}  // namespace sped

@@ -1,248 +1,63 @@
-// operator.cu -- matrix-free symmetry-adapted operator application on the device
-// (kernels K2 diagonal, K3 matvec, K5 expectation of SURVEY 2.2).
+// operator.cu -- host side of the matrix-free operator and the statically compiled kernels
+// (K2 diagonal, K3 matvec with the interpreted canonicalisation program, K5 expectation).
 //
 // Replaces ls_create_interaction{1..4} / ls_create_operator / ls_operator_matmat /
 // ls_operator_expectation of liblattice_symmetries as called from
-// /root/reference/src/SpinED/Internal.hs:260-270,371-381,411-452.
-//
-// Pull form, one row per thread, no atomics, fixed summation order (terms as given, tuples as
-// given, target local configuration ascending):
-//   y[r] = d[r] x[r] + sum_{t,b != a} M_t[a][b] chi(g') (n_s / n_r) x[index(s)],   g'.r' = s,
-// where r' is r with the tuple's bits replaced by b.  Each thread walks its own list of non-zero
-// off-diagonal transitions so that the expensive part (canonicalise + lookup + gather) runs with
-// all lanes of the warp active.
+// /root/reference/src/SpinED/Internal.hs:260-270,371-381,411-452.  The device code of the matvec
+// lives in matvec_kernel.cuh; for symmetric sectors the kernel is normally the run-time
+// specialised one from jit.cpp, the interpreted one below is the same algorithm with the group
+// program read from shared memory.
 #include <algorithm>
 #include <cstring>
 
 #include "device_common.cuh"
+#include "matvec_kernel.cuh"
 
 namespace sped {
 
 ProgramView<u32> program_view32(Basis const& b, size_t& smem, bool& staged);
 ProgramView<u64> program_view64(Basis const& b, size_t& smem, bool& staged);
+void* jit_matvec_kernel(Basis& b, int dtype, int nb);  // jit.cpp; nullptr = not available
 
 namespace {
 
-struct DevBond {
-  std::uint8_t k;
-  std::uint8_t s[4];
-  std::uint8_t pad_;
-  std::uint16_t moff;  // offset (in matrix elements) of this bond's matrix in the pool
-  std::uint16_t zoff;  // offset of its row masks in the mask pool
-  std::uint16_t pad2_[3];
-};
 static_assert(sizeof(DevBond) == 16, "bond records are staged as 16-byte words");
 
-struct TermsView {
-  DevBond const* bonds;
-  double const* pool_re;   // real parts of all matrices, row-major dim x dim each
-  double const* pool_im;   // imaginary parts (same layout)
-  std::uint16_t const* masks;  // per matrix row a: bitmask of b != a with M[a][b] != 0
-  u32 n_bonds;
-  u32 pool_size;
-  u32 mask_size;
+struct TrivialCanon {
+  static constexpr bool symmetric = false;
+  __device__ __forceinline__ void operator()(u64, u64&, int&) const {}
 };
 
-__host__ __device__ inline size_t terms_smem_bytes(TermsView const& t, bool cplx) {
-  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  return up((size_t)t.n_bonds * sizeof(DevBond)) + up((size_t)t.pool_size * 8) * (cplx ? 2 : 1) +
-         up((size_t)t.mask_size * 2);
-}
-
-template <bool CPLX>
-__device__ __forceinline__ TermsView stage_terms(TermsView g, unsigned char* smem) {
-  auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  DevBond* bonds = reinterpret_cast<DevBond*>(smem);
-  unsigned char* p = smem + up((size_t)g.n_bonds * sizeof(DevBond));
-  double* re = reinterpret_cast<double*>(p);
-  p += up((size_t)g.pool_size * 8);
-  double* im = nullptr;
-  if (CPLX) {
-    im = reinterpret_cast<double*>(p);
-    p += up((size_t)g.pool_size * 8);
+template <class W>
+struct ProgramCanon {
+  static constexpr bool symmetric = true;
+  ProgramView<W> P;
+  __device__ __forceinline__ void operator()(u64 x, u64& rep, int& phase) const {
+    W r;
+    u32 step, flipped;
+    canonicalize<W>(P, (W)x, r, step, flipped);
+    rep = r;
+    phase = element_phase<W>(P, step, flipped);
   }
-  std::uint16_t* masks = reinterpret_cast<std::uint16_t*>(p);
-  for (u32 i = threadIdx.x; i < g.n_bonds; i += blockDim.x) bonds[i] = g.bonds[i];
-  for (u32 i = threadIdx.x; i < g.pool_size; i += blockDim.x) {
-    re[i] = g.pool_re[i];
-    if (CPLX) im[i] = g.pool_im[i];
-  }
-  for (u32 i = threadIdx.x; i < g.mask_size; i += blockDim.x) masks[i] = g.masks[i];
-  __syncthreads();
-  TermsView v = g;
-  v.bonds = bonds;
-  v.pool_re = re;
-  v.pool_im = im;
-  v.masks = masks;
-  return v;
-}
-
-// ---- scalar helpers: storage type T <-> accumulator (double or double2) ----
-template <class T> struct Traits;
-template <> struct Traits<float> {
-  using Acc = double;
-  static constexpr bool cplx = false;
-  static __device__ __forceinline__ Acc load(float const* p) { return (double)__ldg(p); }
-  static __device__ __forceinline__ void store(float* p, Acc v) { *p = (float)v; }
-};
-template <> struct Traits<double> {
-  using Acc = double;
-  static constexpr bool cplx = false;
-  static __device__ __forceinline__ Acc load(double const* p) { return __ldg(p); }
-  static __device__ __forceinline__ void store(double* p, Acc v) { *p = v; }
-};
-template <> struct Traits<float2> {
-  using Acc = double2;
-  static constexpr bool cplx = true;
-  static __device__ __forceinline__ Acc load(float2 const* p) { float2 v = __ldg(p); return make_double2(v.x, v.y); }
-  static __device__ __forceinline__ void store(float2* p, Acc v) { *p = make_float2((float)v.x, (float)v.y); }
-};
-template <> struct Traits<double2> {
-  using Acc = double2;
-  static constexpr bool cplx = true;
-  static __device__ __forceinline__ Acc load(double2 const* p) { return __ldg(p); }
-  static __device__ __forceinline__ void store(double2* p, Acc v) { *p = v; }
 };
 
-__device__ __forceinline__ double acc_zero(double) { return 0.0; }
-__device__ __forceinline__ double2 acc_zero(double2) { return make_double2(0.0, 0.0); }
-__device__ __forceinline__ void acc_fma(double& acc, double w, double x) { acc += w * x; }
-__device__ __forceinline__ void acc_fma(double2& acc, double2 w, double2 x) {
-  acc.x += w.x * x.x - w.y * x.y;
-  acc.y += w.x * x.y + w.y * x.x;
-}
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-struct RowContext {
-  BasisIndex index;
-  double const* norm_table;
-  double const* chi_table;  // (cos, sin) pairs
-  u64 row_begin, row_end;   // local rows (global indices)
-};
-
-// Walks the non-zero off-diagonal transitions of row word r in the fixed order and calls
-// sink(bond_index, a, b, flipped_word).  The inner search loop is cheap and may diverge; the sink
-// call site is reached by all lanes that still have work.
-template <class Sink>
-__device__ __forceinline__ void for_each_transition(TermsView const& T, u64 r, Sink&& sink) {
-  u32 bond = 0;
-  u32 bits = 0, a = 0, cur = 0;
-  for (;;) {
-    while (bits == 0 && bond < T.n_bonds) {
-      DevBond const bd = T.bonds[bond];
-      a = 0;
-      for (int j = 0; j < bd.k; ++j) a |= (u32)((r >> bd.s[j]) & 1ull) << (bd.k - 1 - j);
-      bits = T.masks[bd.zoff + a];
-      cur = bond++;
-    }
-    if (bits == 0) break;
-    u32 b = (u32)__ffs((int)bits) - 1u;
-    bits &= bits - 1;
-    DevBond const bd = T.bonds[cur];
-    u32 diff = a ^ b;
-    u64 rp = r;
-    for (int j = 0; j < bd.k; ++j) rp ^= (u64)((diff >> (bd.k - 1 - j)) & 1u) << bd.s[j];
-    sink(cur, a, b, rp);
-  }
-}
-
-struct MatvecParams {
-  RowContext ctx;
-  TermsView terms;
-  double const* diag_re;  // local rows
-  double const* diag_im;  // nullptr when the diagonal is real
-  void const* x;          // replicated, column-major, stride xs
-  void* y;                // local rows, column-major, stride ys
-  u64 xs, ys;
-  u32 ncols;              // columns handled by this launch (<= NB)
-  unsigned long long* counter;  // count mode only
-};
-
-// SYM: non-trivial group (canonicalise).  NB: columns per pass.
+// SYM: non-trivial group (canonicalise with the interpreted program).  NB: columns per pass.
 template <class W, class T, int NB, bool SYM>
-__global__ void __launch_bounds__(kThreads) matvec_kernel(MatvecParams p, ProgramView<W> prog, bool staged) {
-  using TR = Traits<T>;
-  using Acc = typename TR::Acc;
-  constexpr bool CPLX = TR::cplx;
+__global__ void __launch_bounds__(kThreads) matvec_kernel(MatvecParams p, ProgramView<W> prog) {
+  constexpr bool CPLX = Traits<T>::cplx;
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<CPLX>(p.terms, smem);
-  ProgramView<W> P = prog;
-  if (SYM) P = stage_program<W>(prog, smem + terms_smem_bytes(p.terms, CPLX));
-  BasisIndex const ix = p.ctx.index;
-  T const* x = static_cast<T const*>(p.x);
-  T* y = static_cast<T*>(p.y);
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
-    u64 const r = ix.direct ? row : __ldg(ix.reps + row);
-    double inv_nr = 1.0;
-    if (SYM) inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(ix.stab + row));
-    Acc acc[NB];
-    {
-      double dre = __ldg(p.diag_re + i);
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        acc[c] = acc_zero(Acc{});
-        if (c < (int)p.ncols) {
-          Acc xv = TR::load(x + (u64)c * p.xs + row);
-          if constexpr (CPLX) {
-            double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
-            acc_fma(acc[c], make_double2(dre, dim_), xv);
-          } else {
-            acc_fma(acc[c], dre, xv);
-          }
-        }
-      }
-    }
-    for_each_transition(terms, r, [&](u32 bond, u32 a, u32 b, u64 rp) {
-      DevBond const bd = terms.bonds[bond];
-      u32 const dim = 1u << bd.k;
-      u64 rep = rp;
-      u32 step = 0, flipped = 0;
-      if (SYM) {
-        W rw;
-        canonicalize<W>(P, (W)rp, rw, step, flipped);
-        rep = rw;
-      }
-      u64 idx = lookup_index(ix, rep);
-      if (idx == ~0ull) return;
-      double hre = terms.pool_re[bd.moff + a * dim + b];
-      double scale = 1.0;
-      if (SYM) scale = __ldg(p.ctx.norm_table + __ldg(ix.stab + idx)) * inv_nr;
-      if constexpr (CPLX) {
-        double2 w = make_double2(hre, terms.pool_im[bd.moff + a * dim + b]);
-        if (SYM) {
-          std::int32_t ph = element_phase<W>(P, step, flipped);
-          double2 chi = make_double2(__ldg(p.ctx.chi_table + 2 * ph), __ldg(p.ctx.chi_table + 2 * ph + 1));
-          w = cmul(w, chi);
-          w.x *= scale;
-          w.y *= scale;
-        }
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
-      } else {
-        double w = hre;
-        if (SYM) {
-          std::int32_t ph = element_phase<W>(P, step, flipped);
-          w = (ph == 0 ? w : -w) * scale;
-        }
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
-      }
-    });
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-      if (c < (int)p.ncols) TR::store(y + (u64)c * p.ys + i, acc[c]);
+  if constexpr (SYM) {
+    ProgramCanon<W> canon{stage_program<W>(prog, smem + terms_smem_bytes(p.terms, CPLX))};
+    matvec_rows<T, NB>(p, terms, canon);
+  } else {
+    matvec_rows<T, NB>(p, terms, TrivialCanon());
   }
 }
 
 // Counts off-diagonal transitions whose target is in the basis (E of SURVEY 8d).
 template <class W, bool SYM>
-__global__ void __launch_bounds__(kThreads) count_kernel(MatvecParams p, ProgramView<W> prog, bool staged) {
+__global__ void __launch_bounds__(kThreads) count_kernel(MatvecParams p, ProgramView<W> prog) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(p.terms, smem);
   ProgramView<W> P = prog;
@@ -253,7 +68,7 @@ __global__ void __launch_bounds__(kThreads) count_kernel(MatvecParams p, Program
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
     u64 const row = p.ctx.row_begin + i;
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
-    for_each_transition(terms, r, [&](u32, u32, u32, u64 rp) {
+    for_each_transition(terms, r, [&](DevBond const&, u32, u32, u64 rp) {
       u64 rep = rp;
       if (SYM) {
         W rw;
@@ -281,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) diagonal_kernel(RowContext ctx, Term
     for (u32 bnd = 0; bnd < terms.n_bonds; ++bnd) {
       DevBond const bd = terms.bonds[bnd];
       u32 a = 0;
-      for (int j = 0; j < bd.k; ++j) a |= (u32)((r >> bd.s[j]) & 1ull) << (bd.k - 1 - j);
+      for (u32 j = 0; j < bd.k; ++j) a |= (u32)((r >> ((bd.sites >> (8 * j)) & 0xffu)) & 1ull) << (bd.k - 1 - j);
       u32 const dim = 1u << bd.k;
       re += terms.pool_re[bd.moff + a * dim + a];
       im += terms.pool_im[bd.moff + a * dim + a];
@@ -352,8 +167,8 @@ PackedTerms pack_terms(std::vector<Interaction> const& terms) {
     size_t count = t.sites.size() / t.k;
     for (size_t s = 0; s < count; ++s) {
       DevBond b{};
-      b.k = (std::uint8_t)t.k;
-      for (int j = 0; j < t.k; ++j) b.s[j] = (std::uint8_t)t.sites[s * t.k + j];
+      b.k = (u32)t.k;
+      for (int j = 0; j < t.k; ++j) b.sites |= (u32)t.sites[s * t.k + j] << (8 * j);
       b.moff = (std::uint16_t)moff;
       b.zoff = (std::uint16_t)zoff;
       pk.bonds.push_back(b);
@@ -362,13 +177,8 @@ PackedTerms pack_terms(std::vector<Interaction> const& terms) {
   return pk;
 }
 
-struct TermsDevice {
-  TermsView view;
-};
-
 // layout of Operator::d_terms: [bonds][pool_re][pool_im][masks]
-TermsView terms_view(Operator const& op, PackedTerms const* pk_sizes, u32 n_bonds, u32 pool, u32 masks) {
-  (void)pk_sizes;
+TermsView terms_view(Operator const& op, u32 n_bonds, u32 pool, u32 masks) {
   auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
   unsigned char* base = op.d_terms.ptr;
   TermsView v;
@@ -406,15 +216,15 @@ void set_smem(K kernel, size_t smem) {
 }
 
 template <class W, class T, int NB, bool SYM>
-void launch_matvec_t(MatvecParams const& p, ProgramView<W> prog, bool staged, size_t smem, int grid, cudaStream_t s) {
+void launch_matvec_t(MatvecParams const& p, ProgramView<W> prog, size_t smem, int grid, cudaStream_t s) {
   auto k = matvec_kernel<W, T, NB, SYM>;
   set_smem(k, smem);
-  k<<<grid, kThreads, smem, s>>>(p, prog, staged);
+  k<<<grid, kThreads, smem, s>>>(p, prog);
   KERNEL_LAUNCHED();
 }
 
 template <class T>
-void launch_matvec(Operator& op, MatvecParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
+void launch_matvec(Operator& op, MatvecParams p, int dtype, u64 block, u64 xs, u64 ys, cudaStream_t s) {
   Basis& b = *op.basis;
   bool const sym = !b.trivial();
   constexpr bool CPLX = Traits<T>::cplx;
@@ -429,20 +239,27 @@ void launch_matvec(Operator& op, MatvecParams p, u64 block, u64 xs, u64 ys, cuda
     p.y = y + c0 * ys;
     bool wide = left > 1;
     p.ncols = (u32)std::min<u64>(left, wide ? 4 : 1);
-    if (!sym) {
+    void* jit = sym ? jit_matvec_kernel(b, dtype, wide ? 4 : 1) : nullptr;
+    if (jit) {
+      // run-time specialised kernel: same device code, canonicalisation emitted as straight-line code
+      void* args[] = {&p};
+      if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(jit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      CUDA_CHECK(cudaLaunchKernel(jit, dim3(grid), dim3(kThreads), args, tsm, s));
+      KERNEL_LAUNCHED();
+    } else if (!sym) {
       ProgramView<u64> none{};
-      if (wide) launch_matvec_t<u64, T, 4, false>(p, none, false, tsm, grid, s);
-      else launch_matvec_t<u64, T, 1, false>(p, none, false, tsm, grid, s);
+      if (wide) launch_matvec_t<u64, T, 4, false>(p, none, tsm, grid, s);
+      else launch_matvec_t<u64, T, 1, false>(p, none, tsm, grid, s);
     } else if (b.use32()) {
       size_t psm; bool staged;
       auto prog = program_view32(b, psm, staged);
-      if (wide) launch_matvec_t<u32, T, 4, true>(p, prog, staged, tsm + psm, grid, s);
-      else launch_matvec_t<u32, T, 1, true>(p, prog, staged, tsm + psm, grid, s);
+      if (wide) launch_matvec_t<u32, T, 4, true>(p, prog, tsm + psm, grid, s);
+      else launch_matvec_t<u32, T, 1, true>(p, prog, tsm + psm, grid, s);
     } else {
       size_t psm; bool staged;
       auto prog = program_view64(b, psm, staged);
-      if (wide) launch_matvec_t<u64, T, 4, true>(p, prog, staged, tsm + psm, grid, s);
-      else launch_matvec_t<u64, T, 1, true>(p, prog, staged, tsm + psm, grid, s);
+      if (wide) launch_matvec_t<u64, T, 4, true>(p, prog, tsm + psm, grid, s);
+      else launch_matvec_t<u64, T, 1, true>(p, prog, tsm + psm, grid, s);
     }
     c0 += p.ncols;
   }
@@ -512,7 +329,7 @@ void Operator::prepare() {
   u64 n_local = row_end - row_begin;
   d_diag.alloc(std::max<u64>(1, n_local * (real_diagonal ? 1 : 2)));
   OpShape sh = shape_of(*this);
-  TermsView tv = terms_view(*this, nullptr, sh.n_bonds, sh.pool, sh.masks);
+  TermsView tv = terms_view(*this, sh.n_bonds, sh.pool, sh.masks);
   RowContext ctx{b.index, b.d_norm_table.ptr, b.d_chi_table.ptr, row_begin, row_end};
   size_t smem = terms_smem_bytes(tv, true);
   set_smem(diagonal_kernel, smem);
@@ -532,7 +349,7 @@ static MatvecParams make_params(Operator& op) {
   OpShape sh = shape_of(op);
   MatvecParams p{};
   p.ctx = RowContext{b.index, b.d_norm_table.ptr, b.d_chi_table.ptr, op.row_begin, op.row_end};
-  p.terms = terms_view(op, nullptr, sh.n_bonds, sh.pool, sh.masks);
+  p.terms = terms_view(op, sh.n_bonds, sh.pool, sh.masks);
   u64 n_local = op.row_end - op.row_begin;
   p.diag_re = op.d_diag.ptr;
   p.diag_im = op.real_diagonal ? nullptr : op.d_diag.ptr + n_local;
@@ -549,10 +366,10 @@ void Operator::matmat_device(int dtype, u64 block, void const* x, u64 xs, void* 
   p.xs = xs;
   p.ys = ys;
   switch (dtype) {
-    case SPED_F32: launch_matvec<float>(*this, p, block, xs, ys, s); break;
-    case SPED_F64: launch_matvec<double>(*this, p, block, xs, ys, s); break;
-    case SPED_C64: launch_matvec<float2>(*this, p, block, xs, ys, s); break;
-    case SPED_C128: launch_matvec<double2>(*this, p, block, xs, ys, s); break;
+    case SPED_F32: launch_matvec<float>(*this, p, dtype, block, xs, ys, s); break;
+    case SPED_F64: launch_matvec<double>(*this, p, dtype, block, xs, ys, s); break;
+    case SPED_C64: launch_matvec<float2>(*this, p, dtype, block, xs, ys, s); break;
+    case SPED_C128: launch_matvec<double2>(*this, p, dtype, block, xs, ys, s); break;
     default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
   }
 }
@@ -572,17 +389,17 @@ void Operator::count_elements(u64& rows, u64& offdiag) {
       int grid = persistent_grid(n_local, kThreads, 8);
       if (b.trivial()) {
         set_smem(count_kernel<u64, false>, tsm);
-        count_kernel<u64, false><<<grid, kThreads, tsm>>>(p, ProgramView<u64>{}, false);
+        count_kernel<u64, false><<<grid, kThreads, tsm>>>(p, ProgramView<u64>{});
       } else if (b.use32()) {
         size_t psm; bool staged;
         auto prog = program_view32(b, psm, staged);
         set_smem(count_kernel<u32, true>, tsm + psm);
-        count_kernel<u32, true><<<grid, kThreads, tsm + psm>>>(p, prog, staged);
+        count_kernel<u32, true><<<grid, kThreads, tsm + psm>>>(p, prog);
       } else {
         size_t psm; bool staged;
         auto prog = program_view64(b, psm, staged);
         set_smem(count_kernel<u64, true>, tsm + psm);
-        count_kernel<u64, true><<<grid, kThreads, tsm + psm>>>(p, prog, staged);
+        count_kernel<u64, true><<<grid, kThreads, tsm + psm>>>(p, prog);
       }
       KERNEL_LAUNCHED();
       CUDA_CHECK(cudaGetLastError());
@@ -612,8 +429,7 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   if (stage_y.count < padded * block * es) stage_y.alloc(padded * block * es);
   DeviceBuffer<unsigned char>&dx = stage_x, &dy = stage_y;
   CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
-  u64 n_local = row_end - row_begin;
-  // y columns are laid out with stride `padded`; column c of the local block sits at chunk*rank
+  // y columns are laid out with stride `padded`; the local block of column c sits at chunk * rank
   if (!cm.active()) {
     matmat_device(dtype, block, dx.ptr, size, dy.ptr, padded, nullptr);
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -626,7 +442,6 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
     }
     CUDA_CHECK(cudaStreamSynchronize(cm.stream));
   }
-  (void)n_local;
   CUDA_CHECK(cudaMemcpy2D(y, ys * es, dy.ptr, padded * es, size * es, block, cudaMemcpyDeviceToHost));
 }
 
@@ -639,23 +454,24 @@ void Operator::expectation_host(int dtype, u64 size, u64 block, void const* x, u
   if (block == 0 || size == 0) return;
   size_t es = dtype_size(dtype);
   u64 n_local = row_end - row_begin;
-  DeviceBuffer<unsigned char> dx(size * block * es), dy(std::max<u64>(1, n_local) * block * es);
+  u64 ldy = std::max<u64>(1, n_local);
+  DeviceBuffer<unsigned char> dx(size * block * es), dy(ldy * block * es);
   CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
-  matmat_device(dtype, block, dx.ptr, size, dy.ptr, std::max<u64>(1, n_local), nullptr);
-  int grid = persistent_grid(std::max<u64>(1, n_local), kThreads, 4);
+  matmat_device(dtype, block, dx.ptr, size, dy.ptr, ldy, nullptr);
+  int grid = persistent_grid(ldy, kThreads, 4);
   DeviceBuffer<double2> d_partial((size_t)grid * block);
   switch (dtype) {
     case SPED_F32:
-      dot_partial_kernel<float><<<grid, kThreads>>>((float const*)dx.ptr, size, row_begin, (float const*)dy.ptr, std::max<u64>(1, n_local), n_local, (u32)block, d_partial.ptr);
+      dot_partial_kernel<float><<<grid, kThreads>>>((float const*)dx.ptr, size, row_begin, (float const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
       break;
     case SPED_F64:
-      dot_partial_kernel<double><<<grid, kThreads>>>((double const*)dx.ptr, size, row_begin, (double const*)dy.ptr, std::max<u64>(1, n_local), n_local, (u32)block, d_partial.ptr);
+      dot_partial_kernel<double><<<grid, kThreads>>>((double const*)dx.ptr, size, row_begin, (double const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
       break;
     case SPED_C64:
-      dot_partial_kernel<float2><<<grid, kThreads>>>((float2 const*)dx.ptr, size, row_begin, (float2 const*)dy.ptr, std::max<u64>(1, n_local), n_local, (u32)block, d_partial.ptr);
+      dot_partial_kernel<float2><<<grid, kThreads>>>((float2 const*)dx.ptr, size, row_begin, (float2 const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
       break;
     case SPED_C128:
-      dot_partial_kernel<double2><<<grid, kThreads>>>((double2 const*)dx.ptr, size, row_begin, (double2 const*)dy.ptr, std::max<u64>(1, n_local), n_local, (u32)block, d_partial.ptr);
+      dot_partial_kernel<double2><<<grid, kThreads>>>((double2 const*)dx.ptr, size, row_begin, (double2 const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
       break;
     default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
   }

@@ -115,6 +115,8 @@ SIGNATURES = {
     "sped_selftest_small_eigh": (_ci, [_ci, _vp, _vp, _vp]),
     "sped_selftest_program": (_ci, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "sped_selftest_burnside": (_ci, [_vp, C.POINTER(_u64)]),
+    "sped_selftest_jit_source": (_ci, [_vp, _vp, _u64, C.POINTER(_u64)]),
+    "sped_selftest_jit_compile": (_ci, [_vp, _ci, _ci, C.POINTER(_u64)]),
 }
 
 

@@ -199,3 +199,63 @@ def test_config_defaults_and_parsing():
         config.parseDatatype("complex64")
     with pytest.raises(ffi.SpinEDException):
         config.parseConfig({"basis": {"number_spins": 2, "symmetries": []}})
+
+
+def _jit_source(basis):
+    need = C.c_uint64(0)
+    ffi.checkStatus(ffi.lib().sped_selftest_jit_source(basis._ptr, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    ffi.checkStatus(ffi.lib().sped_selftest_jit_source(basis._ptr, buf, need.value, C.byref(need)))
+    return buf.value.decode()
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_square_4x4", "heisenberg_square_5x5",
+                                  "heisenberg_pyrochlore_32", "heisenberg_square_6x6", "heisenberg_chain_42"])
+def test_jit_generated_canonicalisation_matches_oracle(oracle, name, tmp_path):
+    """The straight-line code handed to NVRTC, compiled for the host with g++ (funnel shift
+    emulated), must canonicalise exactly like the oracle."""
+    import subprocess
+
+    cfg = decks.load(name)
+    ob, _ = oracle_problem(oracle, cfg)
+    uc = product_problem(cfg)
+    src = _jit_source(uc.cBasis)
+    shim = r'''
+#include <cstdint>
+typedef unsigned long u64; typedef unsigned int u32;
+#define __device__
+#define __forceinline__ inline
+static inline u32 __funnelshift_l(u32 lo, u32 hi, u32 s) { s &= 31u; return s ? (hi << s) | (lo >> (32u - s)) : hi; }
+namespace sped { typedef ::u64 u64; typedef ::u32 u32; }
+''' + src + r'''
+extern "C" void canon(u64 n, const u64* x, u64* rep, int* phase) {
+  for (u64 i = 0; i < n; ++i) sped::sped_jit_canonicalize(x[i], rep[i], phase[i]);
+}
+'''
+    cpp = tmp_path / "jit_host.cpp"
+    cpp.write_text(shim)
+    so = tmp_path / "jit_host.so"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-shared", "-fPIC", "-o", str(so), str(cpp)])
+    L = C.CDLL(str(so))
+    n, hw = ob.number_spins, ob.hamming_weight
+    rng = np.random.default_rng(99)
+    states = np.array([int(sum(1 << int(p) for p in rng.choice(n, size=hw, replace=False))) for _ in range(400)],
+                      dtype=np.uint64)
+    reps = np.zeros(len(states), dtype=np.uint64)
+    phases = np.zeros(len(states), dtype=np.int32)
+    L.canon(C.c_uint64(len(states)), C.c_void_p(states.ctypes.data), C.c_void_p(reps.ctypes.data), C.c_void_p(phases.ctypes.data))
+    denom = np.lcm.reduce([2] + [oracle.periodicity(s["permutation"]) for s in cfg["basis"]["symmetries"]])
+    for x, r, ph in zip(states, reps, phases):
+        orep, ochi, onorm = ob.state_info(int(x))
+        assert int(r) == orep
+        if onorm > 0:
+            assert abs(np.exp(2j * np.pi * ph / denom) - ochi) < 1e-12
+
+
+def test_jit_kernel_compiles_for_sm_100a_without_a_gpu():
+    uc = product_problem(decks.load("heisenberg_square_4x4"))
+    out = C.c_uint64(0)
+    rc = ffi.lib().sped_selftest_jit_compile(uc.cBasis._ptr, ffi.F64, 1, C.byref(out))
+    if rc != 0:
+        pytest.skip("NVRTC not available here: " + ffi.getErrorMessage(rc))
+    assert out.value > 10000
