@@ -301,6 +301,23 @@ int sped_operator_diagonal(void const* op, double* out) {
   });
 }
 
+int sped_operator_set_cache(void const* op, int mode) {
+  return guard([&] {
+    auto& o = from_handle<Operator>(op);
+    if (mode < -1 || mode > 1) fail(LS_INVALID_ARGUMENT, "cache mode must be -1, 0 or 1");
+    o->drop_cache();
+    o->cache_mode = mode;
+  });
+}
+int sped_operator_cache_info(void const* op, int* ready, uint64_t* bytes, double* build_seconds) {
+  return guard([&] {
+    auto& o = from_handle<Operator>(op);
+    *ready = o->cache_ready ? 1 : 0;
+    *bytes = o->cache_bytes;
+    *build_seconds = o->cache_build_seconds;
+  });
+}
+
 int sped_eigh(void const* op, int dtype, uint64_t n_evals, double eps, int max_basis_size, int max_block_size,
               int min_restart_size, double* evals, void* evecs, double* rnorms, sped_monitor_fn monitor, void* ctx) {
   int status = LS_SUCCESS;

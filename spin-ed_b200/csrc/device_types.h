@@ -64,4 +64,31 @@ struct MatvecParams {
   unsigned long long* counter;  // count mode only
 };
 
+// Operator cache: the non-zero off-diagonal elements of the local rows, kept in HBM once the
+// first matrix-free application has found them.  Rows are grouped in slices of 32 (one warp);
+// inside a slice element j of lane l sits at slice_off[s] + 32 j + l, so a warp reads its
+// column indices with one coalesced 128-byte load per j.
+struct CacheView {
+  u64 const* slice_off;  // [n_slices + 1], in elements
+  u32 const* idx;        // global row index of the target representative
+  dev_u16 const* code;   // index into `table`
+  dev_u16 const* len;    // [local rows] number of stored elements of the row
+  double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
+  u64 n_slices;
+};
+
+struct FillParams {
+  RowContext ctx;
+  TermsView terms;
+  u64 const* slice_off;
+  u32* idx;
+  dev_u16* code;
+  dev_u16* len;
+  dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
+  dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
+  u32 denom;               // number of distinct phases (1 for the trivial group)
+  u32 n_sid;               // number of distinct stabiliser sizes (1 for the trivial group)
+  int* overflow;
+};
+
 }  // namespace sped

@@ -201,6 +201,20 @@ struct Operator {
   DeviceBuffer<unsigned char> d_terms;  // packed bonds + matrices (see operator.cu)
   DeviceBuffer<double> d_diag;          // local rows (real part) [+ imaginary part if !real_diagonal]
   DeviceBuffer<unsigned char> stage_x, stage_y;  // grow-only device staging of the host-pointer entry
+
+  // operator cache (opcache.cu): off-diagonal elements of the local rows resident in HBM
+  int cache_mode = -1;        // -1: auto (build when it fits), 0: never, 1: always try
+  bool cache_ready = false;
+  bool cache_rejected = false;  // decided not to (or failed to) build for this basis generation
+  DeviceBuffer<u64> c_slice_off;
+  DeviceBuffer<u32> c_idx;
+  DeviceBuffer<std::uint16_t> c_code, c_len;
+  DeviceBuffer<double> c_table;
+  u64 c_slices = 0, c_slots = 0, cache_bytes = 0;
+  double cache_build_seconds = 0;
+  bool cache_usable();        // true once the cache is (or has just been) built
+  void drop_cache();
+  void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s);
   u64 row_begin = 0, row_end = 0;
   bool counted = false;
   u64 n_offdiag = 0;

@@ -212,6 +212,7 @@ struct Gen {
 struct Entry {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;
+  cudaKernel_t fill_kernel = nullptr;
   bool failed = false;
 };
 
@@ -293,6 +294,7 @@ Entry compile(Basis& b, int dtype, int nb) {
   }
   cudaError_t e = cudaLibraryLoadData(&out.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.kernel, out.lib, "sped_matvec_jit");
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.fill_kernel, out.lib, "sped_cache_fill_jit");
   if (e != cudaSuccess) {
     std::fprintf(stderr, "[sped] jit: loading the specialised kernel failed (%s), using the interpreted-program kernel\n",
                  cudaGetErrorString(e));
@@ -327,6 +329,15 @@ void* jit_matvec_kernel(Basis& b, int dtype, int nb) {
   auto it = c.entries.find(key);
   if (it == c.entries.end()) it = c.entries.emplace(key, compile(b, dtype, nb)).first;
   return it->second.failed ? nullptr : (void*)it->second.kernel;
+}
+
+// The cache-fill entry point lives in every specialised module; use (or build) the f64 one.
+void* jit_cache_fill_kernel(Basis& b) {
+  if (!jit_matvec_kernel(b, SPED_F64, 1)) return nullptr;
+  std::lock_guard<std::mutex> lock(g_jit_mutex);
+  Cache& c = *static_cast<Cache*>(b.jit_cache.get());
+  auto it = c.entries.find(std::make_pair((int)SPED_F64, 1));
+  return (it == c.entries.end() || it->second.failed) ? nullptr : (void*)it->second.fill_kernel;
 }
 
 }  // namespace sped

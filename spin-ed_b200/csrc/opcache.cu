@@ -1,0 +1,393 @@
+// opcache.cu -- the operator cache: after one matrix-free pass the non-zero off-diagonal elements
+// of the local rows stay resident in HBM (180 GB per B200 is what makes this possible), and every
+// later application of the operator is a coalesced stream of (column, coefficient code) plus the
+// gather of x -- HBM-bound instead of integer-ALU-bound.
+//
+// The reference recomputes every matrix element in every ls_operator_matmat call
+// (/root/reference/src/SpinED/Internal.hs:411-429 is called once per PRIMME block per iteration).
+// Results are bit-identical to the matrix-free kernel: same elements, same order, and the
+// coefficient is rebuilt from the same factors,  w = v * (norm_s * (1 / norm_r)).
+//
+// Layout (sliced ELL): rows in slices of 32 = one warp; element j of lane l of slice s is at
+// slice_off[s] + 32 j + l.  Column indices are u32 (N < 2^32), coefficient codes u16 into a table
+// of (Re v, Im v, norm_s), v = M[a][b] * chi(g').  6 bytes per element.
+#include <chrono>
+#include <cstdlib>
+#include <map>
+
+#include "canon.cuh"
+
+namespace sped {
+
+ProgramView<u32> program_view32(Basis const& b, size_t& smem, bool& staged);
+ProgramView<u64> program_view64(Basis const& b, size_t& smem, bool& staged);
+void* jit_cache_fill_kernel(Basis& b);
+MatvecParams operator_params(Operator& op);
+
+namespace {
+
+// Upper bound of the row lengths (transitions with a non-zero matrix element, whether or not the
+// target survives the projection) and its maximum over each slice.
+__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  TermsView terms = stage_terms<false>(terms_g, smem);
+  u64 const n_local = ctx.row_end - ctx.row_begin;
+  u64 const n_padded = (n_local + 31) & ~(u64)31;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
+    u32 ub = 0;
+    if (i < n_local) {
+      u64 const row = ctx.row_begin + i;
+      u64 const r = ctx.index.direct ? row : __ldg(ctx.index.reps + row);
+      for (u32 bnd = 0; bnd < terms.n_bonds; ++bnd) {
+        DevBond const bd = terms.bonds[bnd];
+        u32 a = 0;
+        for (u32 j = 0; j < bd.k; ++j) a |= (u32)((r >> ((bd.sites >> (8 * j)) & 0xffu)) & 1ull) << (bd.k - 1 - j);
+        ub += __popc((u32)terms.masks[bd.zoff + a]);
+      }
+    }
+    u32 mx = __reduce_max_sync(0xffffffffu, ub);
+    if ((i & 31) == 0) widths[i >> 5] = mx;
+  }
+}
+
+// slice_off[s] = 32 * sum_{t < s} widths[t]   (single block; slices are few millions at most)
+__global__ void __launch_bounds__(1024) slice_scan_kernel(u32 const* widths, u64* slice_off, u64 n) {
+  __shared__ u64 partial[1024];
+  u64 per = (n + 1023) / 1024;
+  u64 lo = min(n, (u64)threadIdx.x * per), hi = min(n, lo + per);
+  u64 s = 0;
+  for (u64 i = lo; i < hi; ++i) s += widths[i];
+  partial[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u64 run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      u64 v = partial[i];
+      partial[i] = run;
+      run += v;
+    }
+    slice_off[n] = run * 32;
+  }
+  __syncthreads();
+  u64 run = partial[threadIdx.x];
+  for (u64 i = lo; i < hi; ++i) {
+    slice_off[i] = run * 32;
+    run += widths[i];
+  }
+}
+
+template <class W, bool SYM>
+__global__ void __launch_bounds__(kThreads) cache_fill_kernel(FillParams p, ProgramView<W> prog) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  TermsView terms = stage_terms<false>(p.terms, smem);
+  if constexpr (SYM) {
+    ProgramCanon<W> canon{stage_program<W>(prog, smem + terms_smem_bytes(p.terms, false))};
+    cache_fill_rows(p, terms, canon);
+  } else {
+    cache_fill_rows(p, terms, TrivialCanon());
+  }
+}
+
+// table[c] = (Re v, Im v, norm_s) for code c = (hid * denom + ph) * n_sid + sid; built on the
+// device so that v is rounded exactly like in the matrix-free kernel.
+__global__ void table_kernel(double const* values_re, double const* values_im, double const* chi_table,
+                             double const* norm_table, std::uint16_t const* sid_stab, u32 n_hid, u32 denom, u32 n_sid,
+                             bool cplx, bool sym, double* table) {
+  u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_hid * denom * n_sid) return;
+  u32 sid = c % n_sid, ph = (c / n_sid) % denom, hid = c / (n_sid * denom);
+  double2 v = make_double2(values_re[hid], values_im[hid]);
+  if (sym) {
+    if (cplx) {
+      v = cmul(v, make_double2(chi_table[2 * ph], chi_table[2 * ph + 1]));
+    } else {
+      v.x = ph == 0 ? v.x : -v.x;
+      v.y = 0.0;
+    }
+  }
+  table[3 * c] = v.x;
+  table[3 * c + 1] = v.y;
+  table[3 * c + 2] = sym ? norm_table[sid_stab[sid]] : 1.0;
+}
+
+struct CachedParams {
+  CacheView cache;
+  RowContext ctx;
+  double const* diag_re;
+  double const* diag_im;
+  void const* x;
+  void* y;
+  u64 xs, ys;
+  u32 ncols;
+  int sym;
+};
+
+// y = H x from the cache: one warp per slice, coalesced index/code loads, read-only gathers of x,
+// accumulation in the stored (= matrix-free) order.
+template <class T, int NB>
+__global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p) {
+  typedef Traits<T> TR;
+  typedef typename TR::Acc Acc;
+  constexpr bool CPLX = TR::cplx;
+  T const* x = static_cast<T const*>(p.x);
+  T* y = static_cast<T*>(p.y);
+  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
+    u64 const row = p.ctx.row_begin + i;
+    double inv_nr = 1.0;
+    if (p.sym) inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
+    Acc acc[NB];
+    double dre = __ldg(p.diag_re + i);
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      acc[c] = acc_zero(Acc());
+      if (c < (int)p.ncols) {
+        Acc xv = TR::load(x + (u64)c * p.xs + row);
+        if constexpr (CPLX) {
+          double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
+          acc_fma(acc[c], make_double2(dre, dim_), xv);
+        } else {
+          acc_fma(acc[c], dre, xv);
+        }
+      }
+    }
+    u64 const base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
+    u32 const len = __ldg(p.cache.len + i);
+#pragma unroll 4
+    for (u32 j = 0; j < len; ++j) {
+      u64 const pos = base + (u64)j * 32;
+      u64 const idx = __ldg(p.cache.idx + pos);
+      double const* t = p.cache.table + 3 * (u32)__ldg(p.cache.code + pos);
+      double scale = 1.0;
+      if (p.sym) scale = __ldg(t + 2) * inv_nr;
+      if constexpr (CPLX) {
+        double2 w = make_double2(__ldg(t), __ldg(t + 1));
+        if (p.sym) {
+          w.x *= scale;
+          w.y *= scale;
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+      } else {
+        double w = __ldg(t);
+        if (p.sym) w = w * scale;
+#pragma unroll
+        for (int c = 0; c < NB; ++c)
+          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c < (int)p.ncols) TR::store(y + (u64)c * p.ys + i, acc[c]);
+  }
+}
+
+template <class T>
+void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
+  u64 n_local = p.ctx.row_end - p.ctx.row_begin;
+  int grid = persistent_grid(n_local, kThreads, 8);
+  T const* x = static_cast<T const*>(p.x);
+  T* y = static_cast<T*>(p.y);
+  for (u64 c0 = 0; c0 < block;) {
+    u64 left = block - c0;
+    p.x = x + c0 * xs;
+    p.y = y + c0 * ys;
+    bool wide = left > 1;
+    p.ncols = (u32)std::min<u64>(left, wide ? 4 : 1);
+    if (wide) cached_matvec_kernel<T, 4><<<grid, kThreads, 0, s>>>(p);
+    else cached_matvec_kernel<T, 1><<<grid, kThreads, 0, s>>>(p);
+    KERNEL_LAUNCHED();
+    c0 += p.ncols;
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+int env_cache_mode() {
+  char const* e = std::getenv("SPED_OPERATOR_CACHE");
+  if (!e || !*e) return -1;
+  return e[0] == '0' ? 0 : 1;
+}
+
+}  // namespace
+
+void Operator::drop_cache() {
+  cache_ready = false;
+  cache_rejected = false;
+  c_slice_off.release();
+  c_idx.release();
+  c_code.release();
+  c_len.release();
+  c_table.release();
+  c_slices = c_slots = cache_bytes = 0;
+}
+
+// Builds the cache on first use when allowed and when it fits; afterwards just reports it.
+bool Operator::cache_usable() {
+  if (cache_ready) return true;
+  int mode = cache_mode >= 0 ? cache_mode : env_cache_mode();
+  if (mode == 0 || cache_rejected) return false;
+  Basis& b = *basis;
+  auto reject = [&](char const* why) {
+    SPED_LOG("operator cache not used: %s", why);
+    cache_rejected = true;
+    drop_cache();
+    cache_rejected = true;
+    return false;
+  };
+  if (b.n_states >= 0xffffffffull) return reject("more than 2^32 - 1 representatives");
+  u64 const n_local = row_end - row_begin;
+  if (n_local == 0) return false;
+  auto t0 = std::chrono::steady_clock::now();
+
+  // distinct off-diagonal matrix values -> hid; stabiliser sizes -> sid
+  std::vector<double> values_re, values_im;
+  std::vector<std::uint16_t> hid_map;
+  {
+    std::map<std::pair<double, double>, u32> seen;
+    for (auto const& t : terms) {
+      u32 dim = 1u << t.k;
+      for (u32 a = 0; a < dim; ++a)
+        for (u32 c = 0; c < dim; ++c) {
+          cplx v = t.matrix[a * dim + c];
+          u32 id = 0;
+          if (a != c && v != cplx(0, 0)) {
+            auto key = std::make_pair(v.real(), v.imag());
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+              it = seen.emplace(key, (u32)values_re.size()).first;
+              values_re.push_back(v.real());
+              values_im.push_back(v.imag());
+            }
+            id = it->second;
+          }
+          hid_map.push_back((std::uint16_t)id);
+        }
+    }
+  }
+  if (values_re.empty()) return reject("operator is diagonal");
+  bool const sym = !b.trivial();
+  u64 const order = b.group_order();
+  std::vector<std::uint16_t> sid_map(order + 1, 0), sid_stab;
+  if (sym) {
+    for (u64 s = 1; s <= order; ++s)
+      if (order % s == 0) {
+        sid_map[s] = (std::uint16_t)sid_stab.size();
+        sid_stab.push_back((std::uint16_t)s);
+      }
+  } else {
+    sid_stab.push_back(1);
+  }
+  u32 const denom = sym ? (u32)b.group->denom : 1u;
+  u64 const n_codes = (u64)values_re.size() * denom * sid_stab.size();
+  if (n_codes > 65536) return reject("more than 65536 distinct coefficients");
+
+  // slice widths from the cheap upper bound, then offsets
+  c_slices = (n_local + 31) / 32;
+  MatvecParams mp = operator_params(*this);
+  DeviceBuffer<u32> d_widths(c_slices);
+  size_t tsm = terms_smem_bytes(mp.terms, false);
+  if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+  slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
+  KERNEL_LAUNCHED();
+  c_slice_off.alloc(c_slices + 1);
+  slice_scan_kernel<<<1, 1024>>>(d_widths.ptr, c_slice_off.ptr, c_slices);
+  KERNEL_LAUNCHED();
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
+  u64 need = c_slots * 6 + n_local * 2 + (c_slices + 1) * 8 + n_codes * 24;
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
+  if (need > free_b - free_b / 16) return reject("does not fit in device memory");
+  c_idx.alloc(std::max<u64>(c_slots, 1));
+  c_code.alloc(std::max<u64>(c_slots, 1));
+  c_len.alloc(n_local);
+
+  // coefficient table
+  DeviceBuffer<double> d_vre, d_vim;
+  DeviceBuffer<std::uint16_t> d_hid, d_sid_map, d_sid_stab;
+  d_vre.upload(values_re);
+  d_vim.upload(values_im);
+  d_hid.upload(hid_map);
+  d_sid_map.upload(sid_map);
+  d_sid_stab.upload(sid_stab);
+  c_table.alloc(n_codes * 3);
+  bool const cplx_table = !is_real();
+  table_kernel<<<(unsigned)((n_codes + 127) / 128), 128>>>(d_vre.ptr, d_vim.ptr, b.d_chi_table.ptr, b.d_norm_table.ptr,
+                                                          d_sid_stab.ptr, (u32)values_re.size(), denom,
+                                                          (u32)sid_stab.size(), cplx_table, sym, c_table.ptr);
+  KERNEL_LAUNCHED();
+
+  // fill pass: the matrix-free traversal (run-time specialised kernel when available)
+  DeviceBuffer<int> d_flag(1);
+  CUDA_CHECK(cudaMemset(d_flag.ptr, 0, sizeof(int)));
+  FillParams fp{};
+  fp.ctx = mp.ctx;
+  fp.terms = mp.terms;
+  fp.slice_off = c_slice_off.ptr;
+  fp.idx = c_idx.ptr;
+  fp.code = c_code.ptr;
+  fp.len = c_len.ptr;
+  fp.hid_map = d_hid.ptr;
+  fp.sid_map = sym ? d_sid_map.ptr : nullptr;
+  fp.denom = denom;
+  fp.n_sid = (u32)sid_stab.size();
+  fp.overflow = d_flag.ptr;
+  int grid = persistent_grid(n_local, kThreads, 8);
+  void* jit = sym ? jit_cache_fill_kernel(b) : nullptr;
+  if (jit) {
+    void* args[] = {&fp};
+    if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(jit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    CUDA_CHECK(cudaLaunchKernel(jit, dim3(grid), dim3(kThreads), args, tsm, nullptr));
+  } else if (!sym) {
+    if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    cache_fill_kernel<u64, false><<<grid, kThreads, tsm>>>(fp, ProgramView<u64>{});
+  } else if (b.use32()) {
+    size_t psm; bool staged;
+    auto prog = program_view32(b, psm, staged);
+    if (tsm + psm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsm + psm)));
+    cache_fill_kernel<u32, true><<<grid, kThreads, tsm + psm>>>(fp, prog);
+  } else {
+    size_t psm; bool staged;
+    auto prog = program_view64(b, psm, staged);
+    if (tsm + psm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsm + psm)));
+    cache_fill_kernel<u64, true><<<grid, kThreads, tsm + psm>>>(fp, prog);
+  }
+  KERNEL_LAUNCHED();
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaDeviceSynchronize());
+  int overflow = 0;
+  CUDA_CHECK(cudaMemcpy(&overflow, d_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+  if (overflow) return reject("internal: a row exceeded its slot bound");
+  cache_bytes = need;
+  cache_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  cache_ready = true;
+  SPED_LOG("operator cache: %llu slots, %.2f GB, built in %.3f s", (unsigned long long)c_slots, need / 1e9,
+           cache_build_seconds);
+  return true;
+}
+
+void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s) {
+  Basis& b = *basis;
+  MatvecParams mp = operator_params(*this);
+  CachedParams p{};
+  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_table.ptr, c_slices};
+  p.ctx = mp.ctx;
+  p.diag_re = mp.diag_re;
+  p.diag_im = mp.diag_im;
+  p.x = x;
+  p.y = y;
+  p.xs = xs;
+  p.ys = ys;
+  p.sym = b.trivial() ? 0 : 1;
+  switch (dtype) {
+    case SPED_F32: launch_cached<float>(p, block, xs, ys, s); break;
+    case SPED_F64: launch_cached<double>(p, block, xs, ys, s); break;
+    case SPED_C64: launch_cached<float2>(p, block, xs, ys, s); break;
+    case SPED_C128: launch_cached<double2>(p, block, xs, ys, s); break;
+    default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
+  }
+}
+
+}  // namespace sped

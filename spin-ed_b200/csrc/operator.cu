@@ -10,8 +10,7 @@
 #include <algorithm>
 #include <cstring>
 
-#include "device_common.cuh"
-#include "matvec_kernel.cuh"
+#include "canon.cuh"
 
 namespace sped {
 
@@ -22,24 +21,6 @@ void* jit_matvec_kernel(Basis& b, int dtype, int nb);  // jit.cpp; nullptr = not
 namespace {
 
 static_assert(sizeof(DevBond) == 16, "bond records are staged as 16-byte words");
-
-struct TrivialCanon {
-  static constexpr bool symmetric = false;
-  __device__ __forceinline__ void operator()(u64, u64&, int&) const {}
-};
-
-template <class W>
-struct ProgramCanon {
-  static constexpr bool symmetric = true;
-  ProgramView<W> P;
-  __device__ __forceinline__ void operator()(u64 x, u64& rep, int& phase) const {
-    W r;
-    u32 step, flipped;
-    canonicalize<W>(P, (W)x, r, step, flipped);
-    rep = r;
-    phase = element_phase<W>(P, step, flipped);
-  }
-};
 
 // SYM: non-trivial group (canonicalise with the interpreted program).  NB: columns per pass.
 template <class W, class T, int NB, bool SYM>
@@ -341,8 +322,12 @@ void Operator::prepare() {
   }
   CUDA_CHECK(cudaDeviceSynchronize());
   counted = false;
+  drop_cache();
   prepared_generation = b.generation;
 }
+
+static MatvecParams make_params(Operator& op);
+MatvecParams operator_params(Operator& op) { return make_params(op); }
 
 static MatvecParams make_params(Operator& op) {
   Basis& b = *op.basis;
@@ -360,6 +345,11 @@ void Operator::matmat_device(int dtype, u64 block, void const* x, u64 xs, void* 
   prepare();
   if (!dtype_is_complex(dtype) && !is_real()) fail(LS_OPERATOR_IS_COMPLEX, "operator is complex but a real datatype was requested");
   if (block == 0 || row_end == row_begin) return;
+  // steady state: the elements found by the first matrix-free pass are resident in HBM
+  if (cache_usable()) {
+    cached_matmat(dtype, block, x, xs, y, ys, s);
+    return;
+  }
   MatvecParams p = make_params(*this);
   p.x = x;
   p.y = y;

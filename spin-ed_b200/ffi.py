@@ -110,6 +110,8 @@ SIGNATURES = {
     "sped_operator_matmat_device": (_ci, [_vp, _ci, _u64, _vp, _u64, _vp, _u64, _vp]),
     "sped_operator_count_elements": (_ci, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "sped_operator_diagonal": (_ci, [_vp, _vp]),
+    "sped_operator_set_cache": (_ci, [_vp, _ci]),
+    "sped_operator_cache_info": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_u64), C.POINTER(C.c_double)]),
     "sped_eigh": (_ci, [_vp, _ci, _u64, C.c_double, _ci, _ci, _ci, _vp, _vp, _vp, MONITOR_FN, _vp]),
     "sped_eigh_last_stats": (_ci, [_vp, C.POINTER(sped_eigh_stats)]),
     "sped_selftest_small_eigh": (_ci, [_ci, _vp, _vp, _vp]),
@@ -426,6 +428,17 @@ def operatorCountElements(op: Operator):
     r, e = C.c_uint64(0), C.c_uint64(0)
     checkStatus(lib().sped_operator_count_elements(op._ptr, C.byref(r), C.byref(e)))
     return int(r.value), int(e.value)
+
+
+def operatorSetCache(op: Operator, mode: int):
+    """-1: auto (default), 0: always matrix-free, 1: cache whenever it fits."""
+    checkStatus(lib().sped_operator_set_cache(op._ptr, mode))
+
+
+def operatorCacheInfo(op: Operator) -> dict:
+    r, b, s = C.c_int(0), C.c_uint64(0), C.c_double(0)
+    checkStatus(lib().sped_operator_cache_info(op._ptr, C.byref(r), C.byref(b), C.byref(s)))
+    return {"ready": bool(r.value), "bytes": int(b.value), "build_seconds": s.value}
 
 
 def operatorDiagonal(op: Operator) -> np.ndarray:

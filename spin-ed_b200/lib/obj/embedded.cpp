@@ -66,6 +66,33 @@ struct MatvecParams {
   unsigned long long* counter;  // count mode only
 };
 
+// Operator cache: the non-zero off-diagonal elements of the local rows, kept in HBM once the
+// first matrix-free application has found them.  Rows are grouped in slices of 32 (one warp);
+// inside a slice element j of lane l sits at slice_off[s] + 32 j + l, so a warp reads its
+// column indices with one coalesced 128-byte load per j.
+struct CacheView {
+  u64 const* slice_off;  // [n_slices + 1], in elements
+  u32 const* idx;        // global row index of the target representative
+  dev_u16 const* code;   // index into `table`
+  dev_u16 const* len;    // [local rows] number of stored elements of the row
+  double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
+  u64 n_slices;
+};
+
+struct FillParams {
+  RowContext ctx;
+  TermsView terms;
+  u64 const* slice_off;
+  u32* idx;
+  dev_u16* code;
+  dev_u16* len;
+  dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
+  dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
+  u32 denom;               // number of distinct phases (1 for the trivial group)
+  u32 n_sid;               // number of distinct stabiliser sizes (1 for the trivial group)
+  int* overflow;
+};
+
 }  // namespace sped
 )SPEDRAW";
 extern char const k_src_matvec_kernel[] = R"SPEDRAW(
@@ -279,8 +306,44 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
   }
 }
 
+// Fills the operator cache: the same traversal as matvec_rows, but instead of gathering x the
+// (target index, coefficient code) of every element that exists is written to its slot.
+// Consecutive local rows map to consecutive lanes (blockDim and the grid stride are multiples of
+// 32), so a warp owns exactly one slice at a time.
+template <class Canon>
+__device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView const& terms, Canon const& canon) {
+  constexpr bool SYM = Canon::symmetric;
+  BasisIndex const ix = p.ctx.index;
+  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
+    u64 const row = p.ctx.row_begin + i;
+    u64 const r = ix.direct ? row : __ldg(ix.reps + row);
+    u64 const slice = i >> 5;
+    u64 const base = __ldg(p.slice_off + slice) + (i & 31);
+    u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
+    u32 j = 0;
+    for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
+      u64 rep = rp;
+      int ph = 0;
+      if (SYM) canon(rp, rep, ph);
+      u64 idx = lookup_index(ix, rep);
+      if (idx == ~(u64)0) return;
+      if (j >= width) {
+        *p.overflow = 1;
+        return;
+      }
+      u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
+      u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
+      p.idx[base + (u64)j * 32] = (u32)idx;
+      p.code[base + (u64)j * 32] = (dev_u16)((hid * p.denom + (u32)ph) * p.n_sid + sid);
+      ++j;
+    });
+    p.len[i] = (dev_u16)j;
+  }
+}
+
 #if defined(SPED_JIT)
-// ---- run-time specialised entry point (NVRTC): SPED_T, SPED_NB and sped_jit_canonicalize come
+// ---- run-time specialised entry points (NVRTC): SPED_T, SPED_NB and sped_jit_canonicalize come
 // from the generated header "sped_jit_program.h" ----
 struct JitCanon {
   static constexpr bool symmetric = true;
@@ -291,6 +354,12 @@ extern "C" __global__ void __launch_bounds__(256) sped_matvec_jit(MatvecParams p
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<Traits<SPED_T>::cplx>(p.terms, smem);
   matvec_rows<SPED_T, SPED_NB>(p, terms, JitCanon());
+}
+
+extern "C" __global__ void __launch_bounds__(256) sped_cache_fill_jit(FillParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  TermsView terms = stage_terms<false>(p.terms, smem);
+  cache_fill_rows(p, terms, JitCanon());
 }
 #endif
 

@@ -278,3 +278,44 @@ def test_full_size_6x6_properties():
     # linearity
     w = ffi.apply(op, 2.0 * u - 3.0 * v)
     assert rel(w, 2.0 * hu - 3.0 * hv) < 1e-12
+
+
+@pytest.mark.parametrize("name", sorted(ALL_SMALL) + ["heisenberg_square_5x5", "heisenberg_chain_24"])
+def test_operator_cache_is_bit_identical_to_matrix_free(oracle, name):
+    """The HBM-resident operator cache must reproduce the matrix-free kernel bit for bit (same
+    elements, same order, same coefficient arithmetic), for every storage type and block width."""
+    cfg = _cfg(name) if name in ALL_SMALL else decks.load(name)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    op = uc.cHamiltonian.operatorObject
+    n = ffi.getNumberStates(uc.cBasis)
+    dtypes = ([np.float64, np.float32] if ffi.isOperatorReal(op) else []) + [np.complex128, np.complex64]
+    for dt in dtypes:
+        for block in (1, 5):
+            x = np.asfortranarray(np.stack([splitmix_vector(n, 21 + c, dt) for c in range(block)], axis=1))
+            ffi.operatorSetCache(op, 0)
+            free = ffi.apply(op, x)
+            assert not ffi.operatorCacheInfo(op)["ready"]
+            ffi.operatorSetCache(op, 1)
+            cached = ffi.apply(op, x)
+            info = ffi.operatorCacheInfo(op)
+            assert info["ready"] and info["bytes"] > 0
+            assert free.tobytes() == cached.tobytes(), (name, dt, block)
+            again = ffi.apply(op, x)
+            assert again.tobytes() == cached.tobytes()
+
+
+def test_jit_and_interpreted_kernels_agree_bitwise(monkeypatch):
+    cfg = decks.load("heisenberg_square_5x5")
+    n_expected = 208012
+    outs = []
+    for jit in ("1", "0"):
+        monkeypatch.setenv("SPED_JIT", jit)
+        uc = product_problem(cfg)
+        ffi.buildBasis(uc.cBasis)
+        op = uc.cHamiltonian.operatorObject
+        ffi.operatorSetCache(op, 0)
+        assert ffi.getNumberStates(uc.cBasis) == n_expected
+        x = splitmix_vector(n_expected, 5, np.complex128)
+        outs.append(ffi.apply(op, x))
+    assert outs[0].tobytes() == outs[1].tobytes()
