@@ -431,7 +431,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
-    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))
+    # exactly one JSON line on stdout: native libraries (NCCL's version banner) write to fd 1, so
+    # fd 1 is pointed at stderr for the run and the result line goes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
+    rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
+    sys.exit(rc)
 
 
 if __name__ == "__main__":
