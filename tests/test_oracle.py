@@ -1,0 +1,130 @@
+"""Pins the CPU oracle (-m "not gpu").  The upstream numerics cannot be built here,
+so the oracle is checked against (a) the reference's README known answer and Spec.hs facts,
+(b) golden vectors produced by an independent first-principles numpy construction
+(tests/golden/make_golden.py), (c) that construction directly, element by element, and
+(d) the independently computed values listed in SURVEY.md 8(c)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import cmat, extra_configs, oracle_problem
+from spin_ed_b200 import decks
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "small_sectors.json")))
+
+
+def _cfg(name):
+    return extra_configs()[name] if name in extra_configs() else decks.load(name)
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_oracle_matches_golden_vectors(oracle, name):
+    g = GOLDEN[name]
+    ob, terms = oracle_problem(oracle, _cfg(name))
+    ob.build()
+    assert [int(v) for v in ob.states] == g["representatives"]
+    assert np.allclose(ob.norms, g["norms"], rtol=0, atol=1e-15)
+    op = oracle.Operator(ob, terms)
+    assert op.is_real == (not g["complex"])
+    x = np.array([complex(*v) for v in g["x"]])
+    y = np.array([complex(*v) for v in g["y"]])
+    got = op.matmat(x if g["complex"] else x.real.copy())
+    assert np.linalg.norm(got - y) <= 1e-13 * np.linalg.norm(y)
+    ev = np.linalg.eigvalsh(op.to_dense())[: len(g["eigenvalues"])]
+    assert np.allclose(ev, g["eigenvalues"], rtol=0, atol=1e-11)
+    # the bit-by-bit permutation path gives the same basis as the Benes path
+    ob2, _ = oracle_problem(oracle, _cfg(name))
+    ob2.use_naive(True)
+    ob2.build()
+    assert np.array_equal(ob2.states, ob.states) and np.array_equal(ob2.norms, ob.norms)
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "chain_8_k1_complex", "chain_8_chiral_3site"])
+def test_oracle_matrix_elements_equal_dense_projection(oracle, name):
+    from oracle import dense_truth as D
+
+    cfg = _cfg(name)
+    b = cfg["basis"]
+    terms = [{"matrix": cmat(t["matrix"]), "sites": t["sites"]} for t in cfg["hamiltonian"]["terms"]]
+    reps, norms, Ht = D.symmetric_hamiltonian(b["number_spins"], b.get("hamming_weight"), b.get("spin_inversion"),
+                                              b["symmetries"], terms)
+    ob, oterms = oracle_problem(oracle, cfg)
+    ob.build()
+    Ho = oracle.Operator(ob, oterms).to_dense()
+    assert np.abs(Ho - Ht).max() < 1e-13
+    assert np.abs(Ho - Ho.conj().T).max() < 1e-13
+
+
+def test_readme_known_answer(oracle):
+    # /root/reference/README.md:37-95
+    ob, terms = oracle_problem(oracle, decks.load("heisenberg_chain_4"))
+    ob.build()
+    assert ob.number_states == 16
+    assert abs(np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())[0] + 8.0) < 1e-12
+
+
+def test_spec_hs_structural_facts(oracle):
+    # /root/reference/test/Spec.hs:38-43,72-79
+    assert oracle.periodicity([3, 2, 1, 0]) == 2
+    assert oracle.periodicity([4, 3, 4, 1]) == -1
+    with pytest.raises(oracle.OracleError):
+        oracle.Basis(5, None, None, [{"permutation": [4, 3, 2, 1, 0], "sector": 3}])
+    d4 = [{"permutation": [3, 2, 1, 0], "sector": 0}, {"permutation": [1, 2, 3, 0], "sector": 0}]
+    assert oracle.Basis(4, 2, None, d4).group_size == 8
+    with pytest.raises(oracle.OracleError) as e:
+        oracle.Basis(4, 2, None, [d4[0], {"permutation": [1, 2, 3, 0], "sector": 1}])
+    assert e.value.code == 11
+
+
+@pytest.mark.parametrize("name,dim", [("heisenberg_square_4x4", 107), ("heisenberg_triangular_19", 4862),
+                                      ("heisenberg_square_5x5", 208012), ("heisenberg_chain_24", 2704156),
+                                      ("xxz_triangular_19", 524288)])
+def test_sector_dimensions_of_survey(oracle, name, dim):
+    ob, _ = oracle_problem(oracle, decks.load(name))
+    ob.build()
+    assert ob.number_states == dim
+    s = ob.states
+    assert np.all(s[1:] > s[:-1])
+
+
+def test_survey_energies(oracle):
+    import scipy.sparse.linalg as sla
+
+    for name, e0 in [("heisenberg_square_4x4", -44.9139328337), ("heisenberg_chain_24", -42.6800580661)]:
+        ob, terms = oracle_problem(oracle, decks.load(name))
+        ob.build()
+        op = oracle.Operator(ob, terms)
+        n = ob.number_states
+        A = sla.LinearOperator((n, n), matvec=lambda v: op.matmat(np.ascontiguousarray(v, dtype=np.float64)), dtype=np.float64)
+        ev = sla.eigsh(A, k=1, which="SA", tol=1e-11)[0]
+        assert abs(ev[0] - e0) < 1e-8
+
+
+def test_symmetric_sector_spectrum_is_subset_of_unsymmetrised(oracle):
+    cfg = decks.chain(12, 6, 1, (0, 0))
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    sym = np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())
+    plain_cfg = decks.chain(12, 6)
+    ob2, terms2 = oracle_problem(oracle, plain_cfg)
+    ob2.build()
+    full = np.linalg.eigvalsh(oracle.Operator(ob2, terms2).to_dense())
+    for v in sym:
+        assert np.min(np.abs(full - v)) < 1e-10
+
+
+def test_expectation_and_block_layout(oracle):
+    ob, terms = oracle_problem(oracle, decks.load("heisenberg_chain_10"))
+    ob.build()
+    op = oracle.Operator(ob, terms)
+    rng = np.random.default_rng(0)
+    X = np.asfortranarray(rng.standard_normal((13, 3)))
+    Y = op.matmat(X)
+    for c in range(3):
+        assert np.allclose(Y[:, c], op.matmat(X[:, c].copy()))
+    assert np.allclose(op.expectation(X), [X[:, c] @ Y[:, c] for c in range(3)])
+    y32 = op.matmat(X.astype(np.float32))
+    assert y32.dtype == np.float32 and np.allclose(y32, Y, rtol=1e-5, atol=1e-5)
