@@ -98,7 +98,7 @@ def cpu_sample_rate(O, oop, n, seconds, dtype=np.float64):
     """Time the oracle matvec on a strided row sample sized for about `seconds` of CPU work."""
     from helpers import splitmix_vector
 
-    x = splitmix_vector(n, 0x5EED0001, dtype)
+    x = splitmix_vector(n, 0x5EED0001, np.float64).astype(dtype)  # real-valued, like the device generator
     x /= np.linalg.norm(x)
     y = np.zeros_like(x)
     probe = min(n, 512 * O.num_threads())
@@ -209,12 +209,12 @@ def run_ours(args):
     t_dtype = torch.float64 if is_real else torch.complex128
     tag = ffi.DTYPE_TAGS[np.dtype(np_dtype)]
     es = np.dtype(np_dtype).itemsize
-    rows, n_off = ffi.operatorCountElements(op)
+    rows = n
     row0, row1 = ffi.basisLocalRows(basis)
     n_local = row1 - row0
     chunk = -(-n // world)
     symmetric = ffi.basisProgramStats(basis)["steps"] > 1 or cfg["basis"].get("spin_inversion") is not None
-    log(f"[rank {rank}] {args.config}: N={n} E={n_off} local rows [{row0},{row1}) build {build_wall:.3f}s")
+    log(f"[rank {rank}] {args.config}: N={n} local rows [{row0},{row1}) build {build_wall:.3f}s")
 
     # device-resident inputs: the replicated vector (padded to world * chunk) and the local output
     # x[i] = uniform(-1,1) from splitmix64(seed ^ global row), generated on the device
@@ -279,6 +279,7 @@ def run_ours(args):
         step()
     barrier()
     cache_info = ffi.operatorCacheInfo(op)
+    rows, n_off = ffi.operatorCountElements(op)  # E: off-diagonal elements one application touches
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -369,7 +370,7 @@ def run_ours(args):
         st = ffi.eighLastStats(op)
         extra.update({"time_to_ground_state_s": time.perf_counter() - t0, "eigenvalues": [float(v) for v in evals],
                       "residual_norms": [float(v) for v in rnorms], "eigh_matvecs": st["matvecs"],
-                      "eigh_restarts": st["restarts"], "eigh_seconds_matvec": st["seconds_matvec"],
+                      "eigh_restarts": st["restarts"], "eigh_seconds_matvec": st["seconds_matvec"], "eigh_stats": st,
                       "eigh_dtype": "f64 (deck asks " + spec.datatype + ")"})
 
     cpu_baseline = None

@@ -189,6 +189,9 @@ typedef struct sped_eigh_stats {
   double seconds_total;
   double seconds_matvec;
   double seconds_ortho;
+  double seconds_residual;
+  double seconds_restart;
+  double seconds_project;
 } sped_eigh_stats;
 int sped_eigh_last_stats(void const* op, sped_eigh_stats* out);
 

@@ -336,6 +336,9 @@ int sped_eigh_last_stats(void const* op, sped_eigh_stats* out) {
     out->seconds_total = s.seconds_total;
     out->seconds_matvec = s.seconds_matvec;
     out->seconds_ortho = s.seconds_ortho;
+    out->seconds_residual = s.seconds_residual;
+    out->seconds_restart = s.seconds_restart;
+    out->seconds_project = s.seconds_project;
   });
 }
 

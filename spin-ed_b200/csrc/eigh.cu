@@ -365,15 +365,16 @@ struct Solver {
   void transform(T* M, int m, int p, std::vector<cplx> const& C) {
     std::vector<double2> c((size_t)m * p);
     for (size_t i = 0; i < c.size(); ++i) c[i] = make_double2(C[i].real(), C[i].imag());
-    DeviceBuffer<double2> dC(c.size());
-    dC.upload(c);
+    if (transform_coeff.count < c.size()) transform_coeff.alloc((size_t)kMaxBasis * kMaxBasis);
+    CUDA_CHECK(cudaMemcpyAsync(transform_coeff.ptr, c.data(), c.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     size_t smem = c.size() * sizeof(double2);
     if (smem > 48 * 1024)
       CUDA_CHECK(cudaFuncSetAttribute(row_transform_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    row_transform_kernel<T><<<grid, kThreads, smem, stream>>>(M, ld, m, p, dC.ptr, n);
+    row_transform_kernel<T><<<grid, kThreads, smem, stream>>>(M, ld, m, p, transform_coeff.ptr, n);
     KERNEL_LAUNCHED();
-    sync();
+    sync();  // `c` is pageable host memory read by the async copy
   }
+  DeviceBuffer<double2> transform_coeff;
 
   int run(u64 k, double eps, int m_max, int b_max, int m_min, double* evals_out, void* evecs_out, double* rnorms_out,
           sped_monitor_fn monitor, void* mctx) {
@@ -421,6 +422,7 @@ struct Solver {
       fail(SPED_INTERNAL_ERROR, "could not generate a new search direction");
     };
     auto extend_projection = [&](int m_old, int m_new) {
+      double t_pr = now_seconds();
       for (int j = m_old; j < m_new; ++j) {
         auto h = dots(V.ptr, m_new, Wm.ptr + (u64)j * ld, true);
         for (int i = 0; i < m_new; ++i) {
@@ -429,6 +431,7 @@ struct Solver {
         }
         Hat(j, j) = Hat(j, j).real();
       }
+      stats.seconds_project += now_seconds() - t_pr;
     };
     int const b0 = std::min<int>(mmax, std::max<int>(b, (int)std::min<u64>(k, (u64)mmax)));
     for (int j = 0; j < b0; ++j) {
@@ -458,7 +461,7 @@ struct Solver {
       std::vector<int> unconverged;
       int n_conv = 0;
       bool have_all = m >= (int)k;
-      // scratch columns: use the tail of Wm's unused columns? keep it simple: dedicated scratch
+      double t_res = now_seconds();
       for (int i = 0; i < kk; ++i) {
         std::vector<double2> s(m);
         for (int j = 0; j < m; ++j) s[j] = make_double2(S[(size_t)j * m + i].real(), S[(size_t)j * m + i].imag());
@@ -477,6 +480,7 @@ struct Solver {
         if (rn[i] <= tol * a_norm) ++n_conv;
         else unconverged.push_back(i);
       }
+      stats.seconds_residual += now_seconds() - t_res;
       if (monitor) {
         sped_eigh_info info{it, m, n_conv, (int)k, stats.matvecs, ev.data(), rn.data(), now_seconds() - t_start};
         if (monitor(&info, mctx) != 0) break;
@@ -495,6 +499,7 @@ struct Solver {
       nb = (int)std::min<u64>((u64)nb, n_global - (u64)m);
       // restart when the new directions do not fit
       if (m + nb > mmax) {
+        double t_rs = now_seconds();
         int r = std::min(std::max(keep, (int)std::min<u64>(k, (u64)m)), mmax - nb);
         r = std::max(r, 1);
         int p_room = mmax - nb - r;
@@ -546,6 +551,7 @@ struct Solver {
         for (int q = 0; q < p; ++q) S[(size_t)q * p + q] = 1.0;
         m = p;
         ++stats.restarts;
+        stats.seconds_restart += now_seconds() - t_rs;
       }
       // remember the current Ritz directions (for the "+k" part of the next restart)
       n_prev = (int)std::min<u64>((u64)std::max(1, std::min(b, (int)k)), (u64)m);

@@ -187,6 +187,7 @@ struct EighStats {
   u64 matvecs = 0;
   int iterations = 0, restarts = 0;
   double seconds_total = 0, seconds_matvec = 0, seconds_ortho = 0;
+  double seconds_residual = 0, seconds_restart = 0, seconds_project = 0;
 };
 
 struct Operator {
@@ -215,6 +216,7 @@ struct Operator {
   bool cache_usable();        // true once the cache is (or has just been) built
   void drop_cache();
   void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s);
+  void cached_count(unsigned long long* d_out);  // adds the local element count to *d_out
   u64 row_begin = 0, row_end = 0;
   bool counted = false;
   u64 n_offdiag = 0;

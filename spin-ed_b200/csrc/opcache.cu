@@ -203,6 +203,13 @@ void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+__global__ void __launch_bounds__(kThreads) sum_len_kernel(std::uint16_t const* len, u64 n, unsigned long long* out) {
+  unsigned long long mine = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) mine += len[i];
+  for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 int env_cache_mode() {
   char const* e = std::getenv("SPED_OPERATOR_CACHE");
   if (!e || !*e) return -1;
@@ -366,6 +373,15 @@ bool Operator::cache_usable() {
   SPED_LOG("operator cache: %llu slots, %.2f GB, built in %.3f s", (unsigned long long)c_slots, need / 1e9,
            cache_build_seconds);
   return true;
+}
+
+// Number of stored elements of the local rows (integer sum: order does not matter).
+void Operator::cached_count(unsigned long long* d_out) {
+  u64 n_local = row_end - row_begin;
+  if (!n_local) return;
+  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local, d_out);
+  KERNEL_LAUNCHED();
+  CUDA_CHECK(cudaGetLastError());
 }
 
 void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s) {

@@ -374,7 +374,9 @@ void Operator::count_elements(u64& rows, u64& offdiag) {
     MatvecParams p = make_params(*this);
     p.counter = d_count.ptr;
     u64 n_local = row_end - row_begin;
-    if (n_local) {
+    if (cache_ready) {
+      cached_count(d_count.ptr);  // the cache holds exactly the elements the matrix-free pass found
+    } else if (n_local) {
       size_t tsm = terms_smem_bytes(p.terms, false);
       int grid = persistent_grid(n_local, kThreads, 8);
       if (b.trivial()) {

@@ -50,7 +50,8 @@ class sped_eigh_info(C.Structure):
 class sped_eigh_stats(C.Structure):
     _fields_ = [
         ("matvecs", C.c_uint64), ("iterations", C.c_int), ("restarts", C.c_int), ("seconds_total", C.c_double),
-        ("seconds_matvec", C.c_double), ("seconds_ortho", C.c_double),
+        ("seconds_matvec", C.c_double), ("seconds_ortho", C.c_double), ("seconds_residual", C.c_double),
+        ("seconds_restart", C.c_double), ("seconds_project", C.c_double),
     ]
 
 

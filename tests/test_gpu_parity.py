@@ -341,3 +341,36 @@ def test_gpu_matches_committed_golden_vectors():
         ev, _, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.complex128 if g["complex"] else np.float64, k)
         scale = max(1.0, abs(g["eigenvalues"][0]))
         assert np.all(np.abs(ev - np.array(g["eigenvalues"][:k])) <= 1e-10 * scale), (name, ev, g["eigenvalues"][:k])
+
+
+def test_degenerate_levels_block_solver(oracle):
+    """Degenerate multiplets: a chain without any symmetry restriction has SU(2) multiplets spread
+    over magnetisation sectors; the block solver must return each level with its multiplicity."""
+    cfg = {"basis": {"number_spins": 10, "symmetries": []}, "hamiltonian": decks.chain(10)["hamiltonian"], "observables": []}
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    want = np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())[:7]
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    ev, vecs, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 7, maxBlockSize=4)
+    assert np.all(np.abs(ev - want) <= 1e-9 * abs(want[0])), (ev, want)
+    assert np.allclose(vecs.T @ vecs, np.eye(7), atol=1e-9)
+
+
+def test_xxz_triangular_19_eigenvectors_are_orthonormal_eigenvectors(oracle):
+    """configs[1]: six lowest states (number_vectors 6, block 6, precision 1e-6).  Multiplicities
+    are certified by the vectors themselves: orthonormal and each an eigenvector (oracle matvec)."""
+    cfg = decks.load("xxz_triangular_19")
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    ev, vecs, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 6, 1.0e-6, 0, 6, 0)
+    assert np.allclose(vecs.T @ vecs, np.eye(6), atol=1e-8)
+    hv = oop.matmat(np.asfortranarray(vecs))
+    a_norm = 20.0
+    for i in range(6):
+        assert np.linalg.norm(hv[:, i] - ev[i] * vecs[:, i]) <= 2e-6 * a_norm, (i, ev)
+    assert abs(ev[0] + 8.6351360078) < 1e-6
+    print("xxz_triangular_19 lowest six:", ev)
