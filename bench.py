@@ -362,6 +362,8 @@ def run_ours(args):
                              "note": "integer-ALU bound: canonicalisation over the symmetry group per element"}}
     if not args.no_eigh:
         ffi.operatorSetCache(op, -1)  # drop the cache: time-to-ground-state includes building it
+        del xfull, xshard, ylocal      # the solver allocates its own vectors (42 spins: 25.6 GB each)
+        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         evals, _, rnorms = ffi.eigh(op, np.dtype(np_dtype), spec.number_vectors, spec.precision, spec.max_primme_basis_size,

@@ -432,6 +432,10 @@ void Basis::build() {
       if (!overflow) {
         comm_group_start();
         for (u64 t = 0; t < n_tiles; ++t) {
+          if (t && t % 64 == 0) {  // keep NCCL groups to a moderate number of operations
+            comm_group_end();
+            comm_group_start();
+          }
           int owner = (int)(t % (u64)cm.world);
           u64 cnt = sc[2 + t];
           if (cnt) {
