@@ -210,23 +210,26 @@ def run_ours(args):
     tag = ffi.DTYPE_TAGS[np.dtype(np_dtype)]
     es = np.dtype(np_dtype).itemsize
     rows = n
-    row0, row1 = ffi.basisLocalRows(basis)
-    n_local = row1 - row0
-    chunk = -(-n // world)
+    rd = ffi.basisRowDistribution(basis)  # block-cyclic rows of this rank, [rank][local] vector layout
+    n_local, chunk = int(rd.n_local), int(rd.chunk)
     symmetric = ffi.basisProgramStats(basis)["steps"] > 1 or cfg["basis"].get("spin_inversion") is not None
-    log(f"[rank {rank}] {args.config}: N={n} local rows [{row0},{row1}) build {build_wall:.3f}s")
+    log(f"[rank {rank}] {args.config}: N={n} local rows {n_local} (blocks of {1 << rd.log2_block}) build {build_wall:.3f}s")
 
     # device-resident inputs: the replicated vector (padded to world * chunk) and the local output
     # x[i] = uniform(-1,1) from splitmix64(seed ^ global row), generated on the device
     # shard by shard so that 40-spin vectors never exist on the host
     def device_splitmix(lo, hi, seed):
+        """values of the local rows lo..hi-1 (local indices), keyed by their GLOBAL row"""
         def s64(v):
             return v - (1 << 64) if v >= (1 << 63) else v
 
         out = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+        lb, bmask = int(rd.log2_block), (1 << int(rd.log2_block)) - 1
         for c0 in range(lo, hi, 1 << 24):
             c1 = min(hi, c0 + (1 << 24))
-            z = (torch.arange(c0, c1, dtype=torch.int64, device=dev) ^ s64(seed)) + s64(0x9E3779B97F4A7C15)
+            i = torch.arange(c0, c1, dtype=torch.int64, device=dev)
+            g = i if world == 1 else ((((i >> lb) * world + rank) << lb) + (i & bmask))
+            z = (g ^ s64(seed)) + s64(0x9E3779B97F4A7C15)
             z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
             z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
             z = z ^ ((z >> 31) & ((1 << 33) - 1))
@@ -235,7 +238,7 @@ def run_ours(args):
 
     xshard = torch.zeros(chunk, dtype=t_dtype, device=dev)
     if n_local:
-        xshard[:n_local] = device_splitmix(row0, row1, 0x5EED0001).to(t_dtype)
+        xshard[:n_local] = device_splitmix(0, n_local, 0x5EED0001).to(t_dtype)
     nrm2 = (xshard.abs() ** 2).sum().to(torch.float64).reshape(1)
     if world > 1:
         dist.all_reduce(nrm2)
@@ -245,7 +248,7 @@ def run_ours(args):
         dist.all_gather_into_tensor(xfull, xshard)
     else:
         xfull.copy_(xshard)
-    if n <= 4096:  # the generator must reproduce the host definition used by the tests
+    if n <= 4096 and world == 1:  # the generator must reproduce the host definition used by the tests
         ref = splitmix_vector(n, 0x5EED0001, np.float64)
         assert np.allclose(xfull[:n].cpu().numpy().real * float(nrm2.sqrt().item()), ref, rtol=0, atol=1e-15)
     ylocal = torch.zeros(max(n_local, 1), dtype=t_dtype, device=dev)
@@ -313,6 +316,11 @@ def run_ours(args):
         b.record()
         barrier()
         kern_ms = a.elapsed_time(b) / args.steps
+    kern_all = [kern_ms]
+    if world > 1:
+        kern_all = [None] * world
+        dist.all_gather_object(kern_all, kern_ms)
+        kern_ms = max(kern_all)  # the slowest rank bounds the step
     peak, peak_src = measured_peak()
     local_off = n_off * n_local / max(n, 1)
     alg_bytes = algorithmic_bytes(n_local, local_off, es, symmetric)
@@ -330,7 +338,12 @@ def run_ours(args):
     if 2 * n * es * world <= args.e2e_host_gb * 1e9:
         y_host = torch.zeros(n, dtype=t_dtype).pin_memory().numpy()
         x_host_t = torch.empty(n, dtype=t_dtype).pin_memory()
-        x_host_t.copy_(xfull[:n])
+        if world == 1:
+            x_host_t.copy_(xfull[:n])
+        else:  # back to global row order for the host-pointer call
+            pos = torch.from_numpy(rd.global_to_position(np.arange(n, dtype=np.uint64)).astype(np.int64)).to(dev)
+            x_host_t.copy_(xfull[pos])
+            del pos
         x_host = x_host_t.numpy()
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -347,7 +360,7 @@ def run_ours(args):
                "d2h_bytes_per_step": n * es}
         # consistency of the two paths (same rows, same data)
         dev_y = ylocal[:n_local].cpu().numpy()
-        if n_local and not np.array_equal(dev_y, y_host[row0:row1]):
+        if n_local and not np.array_equal(dev_y, y_host[rd.local_rows().astype(np.int64)]):
             raise SystemExit("device-resident and host-pointer matvec disagree")
     else:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": n * es, "d2h_bytes_per_step": n * es,
@@ -356,7 +369,7 @@ def run_ours(args):
     mf_achieved = alg_bytes / (matrix_free_ms * 1e-3) / 1e9
     extra = {"basis_build_s": build_wall, "basis_build_device_s": ffi.basisBuildSeconds(basis), "rows": rows,
              "offdiag_elements": n_off, "program": ffi.basisProgramStats(basis), "peak_source": peak_src,
-             "kernel_ms": kern_ms, "operator_cache": cache_info,
+             "kernel_ms": kern_ms, "kernel_ms_per_rank": kern_all, "operator_cache": cache_info,
              "matrix_free": {"ms_per_step": matrix_free_ms, "value": (rows + n_off) / (matrix_free_ms * 1e-3),
                              "unit": UNIT, "roofline_frac_hbm": mf_achieved / peak,
                              "note": "integer-ALU bound: canonicalisation over the symmetry group per element"}}

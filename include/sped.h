@@ -127,12 +127,23 @@ int sped_comm_init(int world_size, int rank, void const* unique_id_128_bytes);
 int sped_comm_finalize(void);
 int sped_comm_rank(void);
 int sped_comm_size(void);
-/* Row block [begin, end) of an N-row problem owned by `rank` of `world` (host logic, no GPU). */
-void sped_row_partition(uint64_t n, int world, int rank, uint64_t* begin, uint64_t* end);
+/* Row distribution (host logic, no GPU).  Rows are dealt to the ranks round-robin in blocks of
+ * 2^log2_block consecutive rows, so that every rank holds the same mix of rows (the sorted
+ * representatives are not homogeneous: contiguous blocks leave the ranks unbalanced).  A rank keeps
+ * its `n_local` rows compactly in local order; the replicated vector handed to
+ * sped_operator_matmat_device is laid out [rank][local index] with every shard padded to `chunk`
+ * entries -- what an all-gather of the local shards produces.  With one rank local == global. */
+typedef struct sped_row_dist {
+  uint64_t n, n_local, chunk;
+  uint32_t world, rank, log2_block, reserved;
+} sped_row_dist;
+void sped_row_distribution(uint64_t n, int world, int rank, sped_row_dist* out);
+uint64_t sped_dist_local_to_global(sped_row_dist const* d, uint64_t local_index);
+uint64_t sped_dist_global_to_position(sped_row_dist const* d, uint64_t global_row);
 
 /* Basis timing / layout queries. */
 int sped_basis_build_seconds(void const* basis, double* out);   /* device time of the last ls_build */
-int sped_basis_local_rows(void const* basis, uint64_t* begin, uint64_t* end);
+int sped_basis_row_distribution(void const* basis, sped_row_dist* out);   /* rows of this rank */
 int sped_basis_device_states(void const* basis, uint64_t const** out_device_ptr);
 /* norms of the representatives as the matvec uses them (host copy, length N) */
 int sped_basis_norms(void const* basis, double* out);
@@ -142,9 +153,10 @@ int sped_basis_state_info(void const* basis, uint64_t count, uint64_t const* sta
 /* Description of the compiled canonicalisation program (steps, rotate-mask ops, delta-swap ops). */
 int sped_basis_program_stats(void const* basis, unsigned* steps, unsigned* rot_ops, unsigned* benes_ops);
 
-/* Device-resident operator application: x_full is the replicated vector [N (padded) x block]
- * and y_local the local row block [rows x block], both DEVICE pointers, column-major.  With one
- * rank this is y = H x.  `stream` is a cudaStream_t (NULL = default stream). */
+/* Device-resident operator application: x_full is the replicated vector, [world * chunk x block]
+ * in the [rank][local] layout of sped_row_dist, y_local the rows of this rank [n_local x block],
+ * both DEVICE pointers, column-major.  With one rank this is plainly y = H x.  `stream` is a
+ * cudaStream_t (NULL = default stream). */
 int sped_operator_matmat_device(void const* op, int dtype, uint64_t block_size, void const* x_full,
                                 uint64_t x_stride, void* y_local, uint64_t y_stride, void* stream);
 /* Number of matrix elements one application touches: rows N and off-diagonal elements E

@@ -224,24 +224,31 @@ int sped_comm_finalize(void) {
 }
 int sped_comm_rank(void) { return comm().rank; }
 int sped_comm_size(void) { return comm().world; }
-void sped_row_partition(uint64_t n, int world, int rank, uint64_t* begin, uint64_t* end) {
-  u64 b, e;
-  row_partition(n, world, rank, b, e);
-  *begin = b;
-  *end = e;
+static_assert(sizeof(sped_row_dist) == sizeof(RowDist), "sped_row_dist mirrors RowDist");
+void sped_row_distribution(uint64_t n, int world, int rank, sped_row_dist* out) {
+  RowDist d = make_row_dist(n, world < 1 ? 1 : world, rank);
+  std::memcpy(out, &d, sizeof d);
+}
+uint64_t sped_dist_local_to_global(sped_row_dist const* d, uint64_t local_index) {
+  RowDist r;
+  std::memcpy(&r, d, sizeof r);
+  return dist_local_to_global(r, local_index);
+}
+uint64_t sped_dist_global_to_position(sped_row_dist const* d, uint64_t global_row) {
+  RowDist r;
+  std::memcpy(&r, d, sizeof r);
+  return dist_global_to_pos(r, global_row);
 }
 
 int sped_basis_build_seconds(void const* basis, double* out) {
   return guard([&] { *out = from_handle<Basis>(basis)->build_seconds; });
 }
-int sped_basis_local_rows(void const* basis, uint64_t* begin, uint64_t* end) {
+int sped_basis_row_distribution(void const* basis, sped_row_dist* out) {
   return guard([&] {
     auto& b = from_handle<Basis>(basis);
     if (!b->built) fail(LS_CACHE_NOT_BUILT, "basis has not been built");
-    u64 lo, hi;
-    b->local_rows(lo, hi);
-    *begin = lo;
-    *end = hi;
+    RowDist d = b->dist();
+    std::memcpy(out, &d, sizeof d);
   });
 }
 int sped_basis_device_states(void const* basis, uint64_t const** out) {
@@ -296,7 +303,7 @@ int sped_operator_diagonal(void const* op, double* out) {
   return guard([&] {
     auto& o = from_handle<Operator>(op);
     o->prepare();
-    u64 n = o->row_end - o->row_begin;
+    u64 n = o->dist.n_local;
     if (n) CUDA_CHECK(cudaMemcpy(out, o->d_diag.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
   });
 }

@@ -132,12 +132,21 @@ void comm_group_end() {
   if (g_comm.active()) nccl_check(api().GroupEnd(), "ncclGroupEnd");
 }
 
-// Rows are dealt in equal chunks of ceil(n / world): every rank but the last owns a full chunk, so
-// an in-place all-gather of fixed-size chunks reproduces the global row order.
-void row_partition(u64 n, int world, int rank, u64& begin, u64& end) {
-  u64 chunk = (n + (u64)world - 1) / (u64)world;
-  begin = std::min(n, chunk * (u64)rank);
-  end = std::min(n, begin + chunk);
+// Block-cyclic row distribution (see RowDist in device_types.h): blocks of 2^log2b rows are dealt
+// round-robin, the block size shrinking for small problems so that every rank still gets work.
+RowDist make_row_dist(u64 n, int world, int rank) {
+  RowDist d{};
+  d.n = n;
+  d.world = (u32)world;
+  d.rank = (u32)rank;
+  u32 lb = 12;
+  while (lb > 5 && (n >> lb) < (u64)world * 64) --lb;
+  d.log2b = lb;
+  d.chunk = 0;
+  for (int r = 0; r < world; ++r) d.chunk = std::max(d.chunk, dist_rows_of(n, (u32)world, (u32)r, lb));
+  d.n_local = dist_rows_of(n, (u32)world, (u32)rank, lb);
+  if (world == 1) d.chunk = n;
+  return d;
 }
 
 }  // namespace sped

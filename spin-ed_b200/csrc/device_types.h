@@ -45,11 +45,51 @@ struct TermsView {
   u32 mask_size;
 };
 
+#if defined(__CUDACC__) || defined(SPED_JIT)
+#define SPED_DIST_FN __host__ __device__ inline
+#else
+#define SPED_DIST_FN inline
+#endif
+
+// Row distribution over ranks: rows are dealt round-robin in blocks of B = 2^log2b consecutive
+// rows (B is a multiple of 32), so every rank holds a statistically identical mix of rows -- the
+// sorted representatives are *not* homogeneous (row length and gather locality drift with the
+// index), and contiguous row blocks leave the ranks badly unbalanced.  A rank stores its rows
+// compactly in local order; the replicated vector is laid out [rank][local index] with every
+// rank's shard padded to `chunk` entries, which is exactly what an NCCL all-gather of the local
+// shards produces.  With one rank local == global.
+struct RowDist {
+  u64 n;        // global number of rows
+  u64 n_local;  // rows owned by this rank
+  u64 chunk;    // padded shard length: max over ranks of rows owned
+  u32 world, rank;
+  u32 log2b;
+  u32 pad_;
+};
+
+SPED_DIST_FN u64 dist_local_to_global(RowDist const& d, u64 i) {
+  if (d.world == 1) return i;
+  u64 blk = i >> d.log2b;
+  return ((blk * d.world + d.rank) << d.log2b) + (i & (((u64)1 << d.log2b) - 1));
+}
+// position of global row g in the replicated [rank][local] layout
+SPED_DIST_FN u64 dist_global_to_pos(RowDist const& d, u64 g) {
+  if (d.world == 1) return g;
+  u64 blk = g >> d.log2b;
+  u64 owner = blk % d.world;
+  return owner * d.chunk + ((blk / d.world) << d.log2b) + (g & (((u64)1 << d.log2b) - 1));
+}
+SPED_DIST_FN u64 dist_rows_of(u64 n, u32 world, u32 rank, u32 log2b) {
+  u64 full = n >> log2b, rem = n & (((u64)1 << log2b) - 1);
+  u64 nb = full / world + (rank < full % world ? 1 : 0);
+  return (nb << log2b) + (rank == full % world ? rem : 0);
+}
+
 struct RowContext {
   BasisIndex index;
   double const* norm_table;  // norm_table[s] = sqrt(s / |G'|)
   double const* chi_table;   // (cos, sin)(2 pi k / denom)
-  u64 row_begin, row_end;    // local rows (global indices)
+  RowDist dist;              // which rows this rank owns
 };
 
 struct MatvecParams {

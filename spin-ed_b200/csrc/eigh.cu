@@ -265,9 +265,10 @@ __device__ __forceinline__ u64 splitmix64(u64 z) {
 
 // uniform(-1, 1) from splitmix64(seed ^ global_row)  (same data for any rank count)
 template <class T>
-__global__ void __launch_bounds__(kThreads) random_kernel(T* w, u64 row0, u64 n, u64 seed) {
+__global__ void __launch_bounds__(kThreads) random_kernel(T* w, RowDist d, u64 seed) {
+  u64 const n = d.n_local;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-    u64 h = splitmix64(seed ^ (row0 + i));
+    u64 h = splitmix64(seed ^ dist_local_to_global(d, i));
     double re = (double)(h >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
     if constexpr (VT<T>::cplx) {
       u64 h2 = splitmix64(h);
@@ -338,7 +339,7 @@ struct Solver {
   }
 
   void randomize(T* w, u64 seed) {
-    random_kernel<T><<<grid, kThreads, 0, stream>>>(w, row0, n, seed);
+    random_kernel<T><<<grid, kThreads, 0, stream>>>(w, op.dist, seed);
     KERNEL_LAUNCHED();
   }
 
@@ -383,9 +384,9 @@ struct Solver {
     Comm& cm = comm();
     n_global = B.n_states;
     op.prepare();
-    row0 = op.row_begin;
-    n = op.row_end - op.row_begin;
-    chunk = (n_global + cm.world - 1) / cm.world;
+    row0 = 0;
+    n = op.dist.n_local;
+    chunk = op.dist.chunk;
     if (k == 0 || k > n_global) fail(LS_INVALID_ARGUMENT, "number of eigenpairs must be in 1..dimension");
     // option defaults
     int b = b_max > 0 ? b_max : (int)std::min<u64>(k, 8);
@@ -602,12 +603,21 @@ struct Solver {
       if (!cm.active()) {
         CUDA_CHECK(cudaMemcpy2D(host, n_global * sizeof(T), V.ptr, ld * sizeof(T), n * sizeof(T), kk, cudaMemcpyDeviceToHost));
       } else {
+        // all-gather gives the [rank][local] layout; the blocks are put back in global row order
+        // on the host (one memcpy per block of 2^log2b rows)
+        std::vector<T> tmp(chunk * cm.world);
+        RowDist const& d = op.dist;
+        u64 const bsz = (u64)1 << d.log2b;
         for (int q = 0; q < kk; ++q) {
           CUDA_CHECK(cudaMemcpyAsync(xfull.ptr + (u64)cm.rank * chunk, V.ptr + (u64)q * ld, n * sizeof(T),
                                      cudaMemcpyDeviceToDevice, stream));
           comm_allgather_inplace(xfull.ptr, chunk * sizeof(T), stream);
-          CUDA_CHECK(cudaMemcpyAsync(host + (u64)q * n_global, xfull.ptr, n_global * sizeof(T), cudaMemcpyDeviceToHost, stream));
+          CUDA_CHECK(cudaMemcpyAsync(tmp.data(), xfull.ptr, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
           sync();
+          for (u64 g0 = 0; g0 < n_global; g0 += bsz) {
+            u64 len = std::min(bsz, n_global - g0);
+            std::memcpy(host + (u64)q * n_global + g0, tmp.data() + dist_global_to_pos(d, g0), len * sizeof(T));
+          }
         }
       }
     }
@@ -628,7 +638,7 @@ int run_solver(Operator& op, int dtype, u64 k, double eps, int m_max, int b_max,
                double* rnorms, sped_monitor_fn monitor, void* ctx) {
   Solver<T> s(op, dtype);
   op.prepare();
-  u64 n = op.row_end - op.row_begin;
+  u64 n = op.dist.n_local;
   s.scratch_buf.alloc(std::max<u64>(n, 1) * std::max<u64>(1, std::min<u64>(k, (u64)kMaxBasis)));
   return s.run(k, eps, m_max, b_max, m_min, evals, evecs, rnorms, monitor, ctx);
 }

@@ -136,7 +136,7 @@ void comm_allreduce_sum_u64(unsigned long long* dev, size_t count, cudaStream_t 
 void comm_broadcast_bytes(void* dev, size_t bytes, int root, cudaStream_t s);
 void comm_group_start();
 void comm_group_end();
-void row_partition(u64 n, int world, int rank, u64& begin, u64& end);
+RowDist make_row_dist(u64 n, int world, int rank);  // block-cyclic row distribution (device_types.h)
 
 // ---- basis (basis.cu) ----
 struct Basis {
@@ -170,7 +170,7 @@ struct Basis {
   void adopt(u64 size, u64 const* host_reps_in);    // K1b
   void finish_build();                              // stabilisers + bucket table
   std::shared_ptr<std::vector<u64>> states_host();
-  void local_rows(u64& b, u64& e) const { row_partition(n_states, comm().world, comm().rank, b, e); }
+  RowDist dist() const { return make_row_dist(n_states, comm().world, comm().rank); }
 };
 
 std::shared_ptr<Basis> make_basis(std::shared_ptr<Group> g, unsigned n_spins, int hw, int inv);
@@ -217,7 +217,7 @@ struct Operator {
   void drop_cache();
   void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s);
   void cached_count(unsigned long long* d_out);  // adds the local element count to *d_out
-  u64 row_begin = 0, row_end = 0;
+  RowDist dist{};  // rows of this rank (fixed at prepare())
   bool counted = false;
   u64 n_offdiag = 0;
   EighStats last_stats;

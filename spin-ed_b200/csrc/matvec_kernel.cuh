@@ -150,9 +150,10 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
   BasisIndex const ix = p.ctx.index;
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  RowDist const dist = p.ctx.dist;
+  u64 const n_local = dist.n_local;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
+    u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     double inv_nr = 1.0;
     if (SYM) inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(ix.stab + row));
@@ -163,7 +164,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
       for (int c = 0; c < NB; ++c) {
         acc[c] = acc_zero(Acc());
         if (c < (int)p.ncols) {
-          Acc xv = TR::load(x + (u64)c * p.xs + row);
+          Acc xv = TR::load(x + (u64)c * p.xs + (u64)dist.rank * dist.chunk + i);
           if constexpr (CPLX) {
             double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
             acc_fma(acc[c], make_double2(dre, dim_), xv);
@@ -180,6 +181,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
       if (SYM) canon(rp, rep, ph);
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
+      u64 const pos = dist_global_to_pos(dist, idx);  // where x[idx] sits in the replicated vector
       double hre = terms.pool_re[bd.moff + a * dim + b];
       double scale = 1.0;
       if (SYM) scale = __ldg(p.ctx.norm_table + __ldg(ix.stab + idx)) * inv_nr;
@@ -193,13 +195,13 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + pos));
       } else {
         double w = hre;
         if (SYM) w = (ph == 0 ? w : -w) * scale;
 #pragma unroll
         for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + pos));
       }
     });
 #pragma unroll
@@ -216,9 +218,10 @@ template <class Canon>
 __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView const& terms, Canon const& canon) {
   constexpr bool SYM = Canon::symmetric;
   BasisIndex const ix = p.ctx.index;
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  RowDist const dist = p.ctx.dist;
+  u64 const n_local = dist.n_local;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
+    u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 const base = __ldg(p.slice_off + slice) + (i & 31);
@@ -236,7 +239,7 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       }
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
-      p.idx[base + (u64)j * 32] = (u32)idx;
+      p.idx[base + (u64)j * 32] = (u32)dist_global_to_pos(dist, idx);  // stored ready for the gather
       p.code[base + (u64)j * 32] = (dev_u16)((hid * p.denom + (u32)ph) * p.n_sid + sid);
       ++j;
     });

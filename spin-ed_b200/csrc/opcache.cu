@@ -31,12 +31,12 @@ namespace {
 __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(terms_g, smem);
-  u64 const n_local = ctx.row_end - ctx.row_begin;
+  u64 const n_local = ctx.dist.n_local;
   u64 const n_padded = (n_local + 31) & ~(u64)31;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
     u32 ub = 0;
     if (i < n_local) {
-      u64 const row = ctx.row_begin + i;
+      u64 const row = dist_local_to_global(ctx.dist, i);
       u64 const r = ctx.index.direct ? row : __ldg(ctx.index.reps + row);
       for (u32 bnd = 0; bnd < terms.n_bonds; ++bnd) {
         DevBond const bd = terms.bonds[bnd];
@@ -131,9 +131,10 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
   constexpr bool CPLX = TR::cplx;
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  u64 const n_local = p.ctx.dist.n_local;
+  u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;  // this rank's shard inside the replicated x
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
+    u64 const row = dist_local_to_global(p.ctx.dist, i);
     double inv_nr = 1.0;
     if (p.sym) inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
     Acc acc[NB];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
     for (int c = 0; c < NB; ++c) {
       acc[c] = acc_zero(Acc());
       if (c < (int)p.ncols) {
-        Acc xv = TR::load(x + (u64)c * p.xs + row);
+        Acc xv = TR::load(x + (u64)c * p.xs + self0 + i);
         if constexpr (CPLX) {
           double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
           acc_fma(acc[c], make_double2(dre, dim_), xv);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
 
 template <class T>
 void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
-  u64 n_local = p.ctx.row_end - p.ctx.row_begin;
+  u64 n_local = p.ctx.dist.n_local;
   int grid = persistent_grid(n_local, kThreads, 8);
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
@@ -242,8 +243,8 @@ bool Operator::cache_usable() {
     cache_rejected = true;
     return false;
   };
-  if (b.n_states >= 0xffffffffull) return reject("more than 2^32 - 1 representatives");
-  u64 const n_local = row_end - row_begin;
+  if (dist.chunk * dist.world >= 0xffffffffull) return reject("replicated vector longer than 2^32 - 1 entries");
+  u64 const n_local = dist.n_local;
   if (n_local == 0) return false;
   auto t0 = std::chrono::steady_clock::now();
 
@@ -377,7 +378,7 @@ bool Operator::cache_usable() {
 
 // Number of stored elements of the local rows (integer sum: order does not matter).
 void Operator::cached_count(unsigned long long* d_out) {
-  u64 n_local = row_end - row_begin;
+  u64 n_local = dist.n_local;
   if (!n_local) return;
   sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local, d_out);
   KERNEL_LAUNCHED();

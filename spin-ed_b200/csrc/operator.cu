@@ -44,10 +44,10 @@ __global__ void __launch_bounds__(kThreads) count_kernel(MatvecParams p, Program
   ProgramView<W> P = prog;
   if (SYM) P = stage_program<W>(prog, smem + terms_smem_bytes(p.terms, false));
   BasisIndex const ix = p.ctx.index;
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  u64 const n_local = p.ctx.dist.n_local;
   unsigned long long mine = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
+    u64 const row = dist_local_to_global(p.ctx.dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     for_each_transition(terms, r, [&](DevBond const&, u32, u32, u64 rp) {
       u64 rep = rp;
@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(kThreads) diagonal_kernel(RowContext ctx, Term
                                                             double* diag_im) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<true>(terms_g, smem);
-  u64 const n_local = ctx.row_end - ctx.row_begin;
+  u64 const n_local = ctx.dist.n_local;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = ctx.row_begin + i;
+    u64 const row = dist_local_to_global(ctx.dist, i);
     u64 const r = ctx.index.direct ? row : __ldg(ctx.index.reps + row);
     double re = 0, im = 0;
     for (u32 bnd = 0; bnd < terms.n_bonds; ++bnd) {
@@ -210,7 +210,7 @@ void launch_matvec(Operator& op, MatvecParams p, int dtype, u64 block, u64 xs, u
   bool const sym = !b.trivial();
   constexpr bool CPLX = Traits<T>::cplx;
   size_t tsm = terms_smem_bytes(p.terms, CPLX);
-  u64 n_local = p.ctx.row_end - p.ctx.row_begin;
+  u64 n_local = p.ctx.dist.n_local;
   int grid = persistent_grid(n_local, kThreads, 8);
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
@@ -306,12 +306,12 @@ void Operator::prepare() {
     std::memcpy(img.data() + off_mask, pk.masks.data(), pk.masks.size() * 2);
   }
   d_terms.upload(img);
-  b.local_rows(row_begin, row_end);
-  u64 n_local = row_end - row_begin;
+  dist = b.dist();
+  u64 n_local = dist.n_local;
   d_diag.alloc(std::max<u64>(1, n_local * (real_diagonal ? 1 : 2)));
   OpShape sh = shape_of(*this);
   TermsView tv = terms_view(*this, sh.n_bonds, sh.pool, sh.masks);
-  RowContext ctx{b.index, b.d_norm_table.ptr, b.d_chi_table.ptr, row_begin, row_end};
+  RowContext ctx{b.index, b.d_norm_table.ptr, b.d_chi_table.ptr, dist};
   size_t smem = terms_smem_bytes(tv, true);
   set_smem(diagonal_kernel, smem);
   if (n_local) {
@@ -333,9 +333,9 @@ static MatvecParams make_params(Operator& op) {
   Basis& b = *op.basis;
   OpShape sh = shape_of(op);
   MatvecParams p{};
-  p.ctx = RowContext{b.index, b.d_norm_table.ptr, b.d_chi_table.ptr, op.row_begin, op.row_end};
+  p.ctx = RowContext{b.index, b.d_norm_table.ptr, b.d_chi_table.ptr, op.dist};
   p.terms = terms_view(op, sh.n_bonds, sh.pool, sh.masks);
-  u64 n_local = op.row_end - op.row_begin;
+  u64 n_local = op.dist.n_local;
   p.diag_re = op.d_diag.ptr;
   p.diag_im = op.real_diagonal ? nullptr : op.d_diag.ptr + n_local;
   return p;
@@ -344,7 +344,7 @@ static MatvecParams make_params(Operator& op) {
 void Operator::matmat_device(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s) {
   prepare();
   if (!dtype_is_complex(dtype) && !is_real()) fail(LS_OPERATOR_IS_COMPLEX, "operator is complex but a real datatype was requested");
-  if (block == 0 || row_end == row_begin) return;
+  if (block == 0 || dist.n_local == 0) return;
   // steady state: the elements found by the first matrix-free pass are resident in HBM
   if (cache_usable()) {
     cached_matmat(dtype, block, x, xs, y, ys, s);
@@ -373,7 +373,7 @@ void Operator::count_elements(u64& rows, u64& offdiag) {
     CUDA_CHECK(cudaMemset(d_count.ptr, 0, 8));
     MatvecParams p = make_params(*this);
     p.counter = d_count.ptr;
-    u64 n_local = row_end - row_begin;
+    u64 n_local = dist.n_local;
     if (cache_ready) {
       cached_count(d_count.ptr);  // the cache holds exactly the elements the matrix-free pass found
     } else if (n_local) {
@@ -405,7 +405,40 @@ void Operator::count_elements(u64& rows, u64& offdiag) {
   offdiag = n_offdiag;
 }
 
-// Host-pointer entry (the reference's PRIMME callback shape): stage x to the device, apply, copy back.
+namespace {
+
+// Conversion between global row order and the replicated [rank][local] layout (device_types.h).
+template <class E>
+__global__ void __launch_bounds__(kThreads) to_dist_kernel(E const* src, E* dst, RowDist d) {
+  for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < d.n; g += (u64)gridDim.x * blockDim.x)
+    dst[dist_global_to_pos(d, g)] = src[g];
+}
+template <class E>
+__global__ void __launch_bounds__(kThreads) from_dist_kernel(E const* src, E* dst, RowDist d) {
+  for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < d.n; g += (u64)gridDim.x * blockDim.x)
+    dst[g] = src[dist_global_to_pos(d, g)];
+}
+
+void convert_layout(bool to_dist, size_t es, void const* src, void* dst, RowDist const& d, cudaStream_t s) {
+  int grid = persistent_grid(std::max<u64>(d.n, 1), kThreads, 8);
+  if (es == 4) {
+    if (to_dist) to_dist_kernel<u32><<<grid, kThreads, 0, s>>>((u32 const*)src, (u32*)dst, d);
+    else from_dist_kernel<u32><<<grid, kThreads, 0, s>>>((u32 const*)src, (u32*)dst, d);
+  } else if (es == 8) {
+    if (to_dist) to_dist_kernel<u64><<<grid, kThreads, 0, s>>>((u64 const*)src, (u64*)dst, d);
+    else from_dist_kernel<u64><<<grid, kThreads, 0, s>>>((u64 const*)src, (u64*)dst, d);
+  } else {
+    if (to_dist) to_dist_kernel<double2><<<grid, kThreads, 0, s>>>((double2 const*)src, (double2*)dst, d);
+    else from_dist_kernel<double2><<<grid, kThreads, 0, s>>>((double2 const*)src, (double2*)dst, d);
+  }
+  KERNEL_LAUNCHED();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+// Host-pointer entry (the reference's PRIMME callback shape): stage x to the device, apply, copy
+// back.  With several ranks every rank passes the full x and receives the full y.
 void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs, void* y, u64 ys) {
   prepare();
   Basis& b = *basis;
@@ -414,27 +447,37 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   if (block == 0 || size == 0) return;
   size_t es = dtype_size(dtype);
   Comm& cm = comm();
-  u64 chunk = (size + cm.world - 1) / cm.world;
-  u64 padded = chunk * cm.world;
+  u64 padded = dist.chunk * dist.world;
   // staging buffers are kept between calls (PRIMME calls this once per block per iteration)
   if (stage_x.count < size * block * es) stage_x.alloc(size * block * es);
-  if (stage_y.count < padded * block * es) stage_y.alloc(padded * block * es);
+  size_t need_y = cm.active() ? 2 * padded * es : size * block * es;
+  if (stage_y.count < need_y) stage_y.alloc(need_y);
   DeviceBuffer<unsigned char>&dx = stage_x, &dy = stage_y;
   CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
-  // y columns are laid out with stride `padded`; the local block of column c sits at chunk * rank
   if (!cm.active()) {
-    matmat_device(dtype, block, dx.ptr, size, dy.ptr, padded, nullptr);
+    matmat_device(dtype, block, dx.ptr, size, dy.ptr, size, nullptr);
     CUDA_CHECK(cudaDeviceSynchronize());
-  } else {
-    // per column: compute the local rows in place inside the padded vector, then all-gather it
-    for (u64 c = 0; c < block; ++c) {
-      unsigned char* col = dy.ptr + c * padded * es;
-      matmat_device(dtype, 1, dx.ptr + c * size * es, size, col + (u64)cm.rank * chunk * es, padded, cm.stream);
-      comm_allgather_inplace(col, chunk * es, cm.stream);
-    }
-    CUDA_CHECK(cudaStreamSynchronize(cm.stream));
+    CUDA_CHECK(cudaMemcpy2D(y, ys * es, dy.ptr, size * es, size * es, block, cudaMemcpyDeviceToHost));
+    return;
   }
-  CUDA_CHECK(cudaMemcpy2D(y, ys * es, dy.ptr, padded * es, size * es, block, cudaMemcpyDeviceToHost));
+  // per column: x -> [rank][local] layout, local rows of y computed in place inside a padded
+  // vector, all-gather, back to global order (written over the x column, which is no longer needed)
+  unsigned char* xp = dy.ptr;
+  unsigned char* yp = dy.ptr + padded * es;
+  for (u64 c = 0; c < block; ++c) {
+    unsigned char* col = dx.ptr + c * size * es;
+    convert_layout(true, es, col, xp, dist, cm.stream);
+    matmat_device(dtype, 1, xp, padded, yp + (u64)cm.rank * dist.chunk * es, padded, cm.stream);
+    comm_allgather_inplace(yp, dist.chunk * es, cm.stream);
+    convert_layout(false, es, yp, col, dist, cm.stream);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(cm.stream));
+  CUDA_CHECK(cudaMemcpy2D(y, ys * es, dx.ptr, size * es, size * es, block, cudaMemcpyDeviceToHost));
+}
+
+template <class T>
+static void launch_dot(void const* x, void const* y, u64 n, double2* partial, int grid) {
+  dot_partial_kernel<T><<<grid, kThreads>>>((T const*)x, 0, 0, (T const*)y, 0, n, 1u, partial);
 }
 
 void Operator::expectation_host(int dtype, u64 size, u64 block, void const* x, u64 xs, cplx* out) {
@@ -445,37 +488,33 @@ void Operator::expectation_host(int dtype, u64 size, u64 block, void const* x, u
   for (u64 c = 0; c < block; ++c) out[c] = cplx(0, 0);
   if (block == 0 || size == 0) return;
   size_t es = dtype_size(dtype);
-  u64 n_local = row_end - row_begin;
-  u64 ldy = std::max<u64>(1, n_local);
-  DeviceBuffer<unsigned char> dx(size * block * es), dy(ldy * block * es);
-  CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
-  matmat_device(dtype, block, dx.ptr, size, dy.ptr, ldy, nullptr);
-  int grid = persistent_grid(ldy, kThreads, 4);
-  DeviceBuffer<double2> d_partial((size_t)grid * block);
-  switch (dtype) {
-    case SPED_F32:
-      dot_partial_kernel<float><<<grid, kThreads>>>((float const*)dx.ptr, size, row_begin, (float const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
-      break;
-    case SPED_F64:
-      dot_partial_kernel<double><<<grid, kThreads>>>((double const*)dx.ptr, size, row_begin, (double const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
-      break;
-    case SPED_C64:
-      dot_partial_kernel<float2><<<grid, kThreads>>>((float2 const*)dx.ptr, size, row_begin, (float2 const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
-      break;
-    case SPED_C128:
-      dot_partial_kernel<double2><<<grid, kThreads>>>((double2 const*)dx.ptr, size, row_begin, (double2 const*)dy.ptr, ldy, n_local, (u32)block, d_partial.ptr);
-      break;
-    default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
-  }
-  KERNEL_LAUNCHED();
-  CUDA_CHECK(cudaGetLastError());
-  auto partial = d_partial.download();
+  u64 n_local = dist.n_local;
+  u64 padded = dist.chunk * dist.world;
+  DeviceBuffer<unsigned char> dx(size * es), xp(padded * es), dy(std::max<u64>(1, n_local) * es);
+  int grid = persistent_grid(std::max<u64>(1, n_local), kThreads, 4);
+  DeviceBuffer<double2> d_partial((size_t)grid);
   std::vector<double> sums(2 * block, 0.0);
-  for (u64 c = 0; c < block; ++c)
-    for (int g = 0; g < grid; ++g) {
-      sums[2 * c] += partial[c * grid + g].x;
-      sums[2 * c + 1] += partial[c * grid + g].y;
+  for (u64 c = 0; c < block; ++c) {
+    CUDA_CHECK(cudaMemcpy(dx.ptr, static_cast<unsigned char const*>(x) + c * xs * es, size * es, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(xp.ptr, 0, padded * es));
+    convert_layout(true, es, dx.ptr, xp.ptr, dist, nullptr);
+    matmat_device(dtype, 1, xp.ptr, padded, dy.ptr, std::max<u64>(1, n_local), nullptr);
+    void const* xl = xp.ptr + (u64)dist.rank * dist.chunk * es;  // this rank's rows of x
+    switch (dtype) {
+      case SPED_F32: launch_dot<float>(xl, dy.ptr, n_local, d_partial.ptr, grid); break;
+      case SPED_F64: launch_dot<double>(xl, dy.ptr, n_local, d_partial.ptr, grid); break;
+      case SPED_C64: launch_dot<float2>(xl, dy.ptr, n_local, d_partial.ptr, grid); break;
+      case SPED_C128: launch_dot<double2>(xl, dy.ptr, n_local, d_partial.ptr, grid); break;
+      default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
     }
+    KERNEL_LAUNCHED();
+    CUDA_CHECK(cudaGetLastError());
+    auto partial = d_partial.download();
+    for (int g = 0; g < grid; ++g) {
+      sums[2 * c] += partial[g].x;
+      sums[2 * c + 1] += partial[g].y;
+    }
+  }
   if (comm().active()) {
     DeviceBuffer<double> d(2 * block);
     d.upload(sums);

@@ -101,9 +101,11 @@ SIGNATURES = {
     "sped_comm_finalize": (_ci, []),
     "sped_comm_rank": (_ci, []),
     "sped_comm_size": (_ci, []),
-    "sped_row_partition": (None, [_u64, _ci, _ci, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sped_row_distribution": (None, [_u64, _ci, _ci, _vp]),
+    "sped_dist_local_to_global": (_u64, [_vp, _u64]),
+    "sped_dist_global_to_position": (_u64, [_vp, _u64]),
     "sped_basis_build_seconds": (_ci, [_vp, C.POINTER(C.c_double)]),
-    "sped_basis_local_rows": (_ci, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "sped_basis_row_distribution": (_ci, [_vp, _vp]),
     "sped_basis_device_states": (_ci, [_vp, _pp]),
     "sped_basis_norms": (_ci, [_vp, _vp]),
     "sped_basis_state_info": (_ci, [_vp, _u64, _vp, _vp, _vp, _vp]),
@@ -368,10 +370,38 @@ def kernelLaunches() -> int:
     return int(lib().sped_kernel_launches())
 
 
-def rowPartition(n: int, world: int, rank: int):
-    b, e = C.c_uint64(0), C.c_uint64(0)
-    lib().sped_row_partition(n, world, rank, C.byref(b), C.byref(e))
-    return int(b.value), int(e.value)
+class RowDist(C.Structure):
+    """``sped_row_dist``: block-cyclic row distribution (include/sped.h)."""
+
+    _fields_ = [("n", C.c_uint64), ("n_local", C.c_uint64), ("chunk", C.c_uint64), ("world", C.c_uint32),
+                ("rank", C.c_uint32), ("log2_block", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def local_to_global(self, local) -> np.ndarray:
+        """Global row indices of local indices (vectorised mirror of sped_dist_local_to_global)."""
+        i = np.asarray(local, dtype=np.uint64)
+        if self.world == 1:
+            return i
+        lb = np.uint64(self.log2_block)
+        mask = np.uint64((1 << self.log2_block) - 1)
+        return (((i >> lb) * np.uint64(self.world) + np.uint64(self.rank)) << lb) + (i & mask)
+
+    def global_to_position(self, rows) -> np.ndarray:
+        g = np.asarray(rows, dtype=np.uint64)
+        if self.world == 1:
+            return g
+        lb = np.uint64(self.log2_block)
+        mask = np.uint64((1 << self.log2_block) - 1)
+        blk = g >> lb
+        return (blk % np.uint64(self.world)) * np.uint64(self.chunk) + ((blk // np.uint64(self.world)) << lb) + (g & mask)
+
+    def local_rows(self) -> np.ndarray:
+        return self.local_to_global(np.arange(self.n_local, dtype=np.uint64))
+
+
+def rowDistribution(n: int, world: int, rank: int) -> RowDist:
+    d = RowDist()
+    lib().sped_row_distribution(n, world, rank, C.byref(d))
+    return d
 
 
 def commUniqueId() -> bytes:
@@ -394,10 +424,10 @@ def basisBuildSeconds(basis: SpinBasis) -> float:
     return out.value
 
 
-def basisLocalRows(basis: SpinBasis):
-    b, e = C.c_uint64(0), C.c_uint64(0)
-    checkStatus(lib().sped_basis_local_rows(basis._ptr, C.byref(b), C.byref(e)))
-    return int(b.value), int(e.value)
+def basisRowDistribution(basis: SpinBasis) -> RowDist:
+    d = RowDist()
+    checkStatus(lib().sped_basis_row_distribution(basis._ptr, C.byref(d)))
+    return d
 
 
 def basisNorms(basis: SpinBasis) -> np.ndarray:
@@ -443,8 +473,7 @@ def operatorCacheInfo(op: Operator) -> dict:
 
 
 def operatorDiagonal(op: Operator) -> np.ndarray:
-    b, e = basisLocalRows(op.basis)
-    out = np.zeros(e - b, dtype=np.float64)
+    out = np.zeros(basisRowDistribution(op.basis).n_local, dtype=np.float64)
     checkStatus(lib().sped_operator_diagonal(op._ptr, out.ctypes.data))
     return out
 

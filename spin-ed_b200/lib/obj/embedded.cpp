@@ -47,11 +47,51 @@ struct TermsView {
   u32 mask_size;
 };
 
+#if defined(__CUDACC__) || defined(SPED_JIT)
+#define SPED_DIST_FN __host__ __device__ inline
+#else
+#define SPED_DIST_FN inline
+#endif
+
+// Row distribution over ranks: rows are dealt round-robin in blocks of B = 2^log2b consecutive
+// rows (B is a multiple of 32), so every rank holds a statistically identical mix of rows -- the
+// sorted representatives are *not* homogeneous (row length and gather locality drift with the
+// index), and contiguous row blocks leave the ranks badly unbalanced.  A rank stores its rows
+// compactly in local order; the replicated vector is laid out [rank][local index] with every
+// rank's shard padded to `chunk` entries, which is exactly what an NCCL all-gather of the local
+// shards produces.  With one rank local == global.
+struct RowDist {
+  u64 n;        // global number of rows
+  u64 n_local;  // rows owned by this rank
+  u64 chunk;    // padded shard length: max over ranks of rows owned
+  u32 world, rank;
+  u32 log2b;
+  u32 pad_;
+};
+
+SPED_DIST_FN u64 dist_local_to_global(RowDist const& d, u64 i) {
+  if (d.world == 1) return i;
+  u64 blk = i >> d.log2b;
+  return ((blk * d.world + d.rank) << d.log2b) + (i & (((u64)1 << d.log2b) - 1));
+}
+// position of global row g in the replicated [rank][local] layout
+SPED_DIST_FN u64 dist_global_to_pos(RowDist const& d, u64 g) {
+  if (d.world == 1) return g;
+  u64 blk = g >> d.log2b;
+  u64 owner = blk % d.world;
+  return owner * d.chunk + ((blk / d.world) << d.log2b) + (g & (((u64)1 << d.log2b) - 1));
+}
+SPED_DIST_FN u64 dist_rows_of(u64 n, u32 world, u32 rank, u32 log2b) {
+  u64 full = n >> log2b, rem = n & (((u64)1 << log2b) - 1);
+  u64 nb = full / world + (rank < full % world ? 1 : 0);
+  return (nb << log2b) + (rank == full % world ? rem : 0);
+}
+
 struct RowContext {
   BasisIndex index;
   double const* norm_table;  // norm_table[s] = sqrt(s / |G'|)
   double const* chi_table;   // (cos, sin)(2 pi k / denom)
-  u64 row_begin, row_end;    // local rows (global indices)
+  RowDist dist;              // which rows this rank owns
 };
 
 struct MatvecParams {
@@ -248,9 +288,10 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
   BasisIndex const ix = p.ctx.index;
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  RowDist const dist = p.ctx.dist;
+  u64 const n_local = dist.n_local;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
+    u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     double inv_nr = 1.0;
     if (SYM) inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(ix.stab + row));
@@ -261,7 +302,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
       for (int c = 0; c < NB; ++c) {
         acc[c] = acc_zero(Acc());
         if (c < (int)p.ncols) {
-          Acc xv = TR::load(x + (u64)c * p.xs + row);
+          Acc xv = TR::load(x + (u64)c * p.xs + (u64)dist.rank * dist.chunk + i);
           if constexpr (CPLX) {
             double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
             acc_fma(acc[c], make_double2(dre, dim_), xv);
@@ -278,6 +319,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
       if (SYM) canon(rp, rep, ph);
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
+      u64 const pos = dist_global_to_pos(dist, idx);  // where x[idx] sits in the replicated vector
       double hre = terms.pool_re[bd.moff + a * dim + b];
       double scale = 1.0;
       if (SYM) scale = __ldg(p.ctx.norm_table + __ldg(ix.stab + idx)) * inv_nr;
@@ -291,13 +333,13 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + pos));
       } else {
         double w = hre;
         if (SYM) w = (ph == 0 ? w : -w) * scale;
 #pragma unroll
         for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + pos));
       }
     });
 #pragma unroll
@@ -314,9 +356,10 @@ template <class Canon>
 __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView const& terms, Canon const& canon) {
   constexpr bool SYM = Canon::symmetric;
   BasisIndex const ix = p.ctx.index;
-  u64 const n_local = p.ctx.row_end - p.ctx.row_begin;
+  RowDist const dist = p.ctx.dist;
+  u64 const n_local = dist.n_local;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = p.ctx.row_begin + i;
+    u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 const base = __ldg(p.slice_off + slice) + (i & 31);
@@ -334,7 +377,7 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       }
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
-      p.idx[base + (u64)j * 32] = (u32)idx;
+      p.idx[base + (u64)j * 32] = (u32)dist_global_to_pos(dist, idx);  // stored ready for the gather
       p.code[base + (u64)j * 32] = (dev_u16)((hid * p.denom + (u32)ph) * p.n_sid + sid);
       ++j;
     });

@@ -37,11 +37,12 @@ def main():
         n = ob.number_states
         uc = product_problem(cfg)
         ffi.buildBasis(uc.cBasis)
-        op = uc.cHamiltonian.operatorObject
         assert ffi.getNumberStates(uc.cBasis) == n
         assert np.array_equal(ffi.basisGetStates(uc.cBasis), ob.states), "representatives differ"
-        b, e = ffi.basisLocalRows(uc.cBasis)
-        assert (b, e) == ffi.rowPartition(n, world, rank)
+        rd = ffi.basisRowDistribution(uc.cBasis)
+        ref = ffi.rowDistribution(n, world, rank)
+        assert (rd.n_local, rd.chunk, rd.log2_block) == (ref.n_local, ref.chunk, ref.log2_block)
+        assert len(ffi.operatorDiagonal(op := uc.cHamiltonian.operatorObject)) == rd.n_local
         dt = np.float64 if oop.is_real else np.complex128
         x = np.asfortranarray(np.stack([splitmix_vector(n, 0x5EED0001 + c, dt) for c in range(2)], axis=1))
         want = oop.matmat(x)

@@ -176,16 +176,35 @@ def test_small_eigh_matches_numpy(m, cplx):
     assert np.allclose(V.conj().T @ V, np.eye(m), atol=1e-12)
 
 
-def test_row_partition_covers_rows_in_equal_chunks():
-    for n in [0, 1, 7, 13, 1000, 861725794]:
+def test_row_distribution_is_a_balanced_block_cyclic_partition():
+    import ctypes as C
+
+    for n in [0, 1, 7, 13, 1000, 70001, 15804956]:
         for world in [1, 2, 3, 8]:
-            spans = [ffi.rowPartition(n, world, r) for r in range(world)]
-            chunk = -(-n // world) if n else 0
-            assert spans[0][0] == 0 and spans[-1][1] == n
+            seen = np.zeros(n, dtype=np.int64)
+            counts = []
+            chunk = None
             for r in range(world):
-                assert spans[r][0] == min(n, r * chunk)
-                if r:
-                    assert spans[r][0] == spans[r - 1][1]
+                d = ffi.rowDistribution(n, world, r)
+                chunk = d.chunk if chunk is None else chunk
+                assert d.chunk == chunk and d.n == n and d.world == world and d.rank == r
+                counts.append(d.n_local)
+                if n <= 70001:
+                    rows = d.local_rows()
+                    assert len(rows) == d.n_local and np.all(np.diff(rows.astype(np.int64)) > 0)
+                    seen[rows.astype(np.int64)] += 1
+                    pos = d.global_to_position(rows)
+                    assert np.array_equal(pos, np.uint64(r * d.chunk) + np.arange(d.n_local, dtype=np.uint64))
+                    for i in (0, d.n_local // 2, d.n_local - 1):  # the C functions agree with the numpy mirror
+                        if d.n_local:
+                            g = ffi.lib().sped_dist_local_to_global(C.byref(d), int(i))
+                            assert g == int(rows[i])
+                            assert ffi.lib().sped_dist_global_to_position(C.byref(d), g) == r * d.chunk + i
+            assert sum(counts) == n and max(counts) == (chunk if world > 1 or n else 0) or n == 0 or world == 1
+            if n <= 70001:
+                assert np.all(seen == 1)
+            if n >= 1000:  # balanced to within one block
+                assert max(counts) - min(counts) <= (1 << ffi.rowDistribution(n, world, 0).log2_block)
 
 
 def test_config_defaults_and_parsing():

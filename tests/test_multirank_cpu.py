@@ -1,5 +1,5 @@
-"""World-size-2 tests on CPU (gloo): the host-side sharding logic of the N > 1 path -- equal-chunk
-row partition, padded in-place all-gather layout, rank/offset bookkeeping -- checked with the
+"""World-size-2 tests on CPU (gloo): the host-side sharding logic of the N > 1 path -- block-cyclic
+row distribution, padded [rank][local] all-gather layout, rank/offset bookkeeping -- checked with the
 oracle standing in for the device kernel (test infrastructure only)."""
 import os
 import sys
@@ -30,26 +30,31 @@ def _worker(rank, world, port, ok):
         ob.build()
         oop = O.Operator(ob, terms)
         n = ob.number_states
-        b, e = ffi.rowPartition(n, world, rank)
-        chunk = -(-n // world)
-        assert b == min(n, rank * chunk) and e == min(n, b + chunk)
+        rd = ffi.rowDistribution(n, world, rank)
+        rows = rd.local_rows().astype(np.int64)  # block-cyclic rows of this rank, ascending
+        chunk, n_loc = int(rd.chunk), int(rd.n_local)
+        assert len(rows) == n_loc
         x = splitmix_vector(n)
-        # every rank owns chunk `rank` of the padded vector; all-gather restores the global order
+        # every rank owns shard `rank` of the padded [rank][local] vector; an all-gather of the
+        # local shards produces exactly that layout
         xfull = torch.zeros(chunk * world, dtype=torch.float64)
         shard = torch.zeros(chunk, dtype=torch.float64)
-        shard[: e - b] = torch.from_numpy(x[b:e].copy())
+        shard[:n_loc] = torch.from_numpy(x[rows].copy())
         dist.all_gather_into_tensor(xfull, shard)
-        assert np.array_equal(xfull[:n].numpy(), x)
-        # local rows of y from the replicated x, then the same gather for y
-        y_local = np.zeros(n)
-        oop.matmat_rows(xfull[:n].numpy().copy(), y_local, b, e, 1)
+        pos = rd.global_to_position(np.arange(n, dtype=np.uint64)).astype(np.int64)
+        assert np.array_equal(xfull.numpy()[pos], x)  # global order is recovered through the position map
+        # local rows of y from the replicated x (oracle row subset), then the same gather for y
+        x_global = xfull.numpy()[pos].copy()
+        y_rows = np.zeros(n)
+        for r in rows:  # oracle entry point takes (lo, hi, stride): one row at a time is fine at this size
+            oop.matmat_rows(x_global, y_rows, int(r), int(r) + 1, 1)
         yshard = torch.zeros(chunk, dtype=torch.float64)
-        yshard[: e - b] = torch.from_numpy(y_local[b:e].copy())
+        yshard[:n_loc] = torch.from_numpy(y_rows[rows].copy())
         yfull = torch.zeros(chunk * world, dtype=torch.float64)
         dist.all_gather_into_tensor(yfull, yshard)
-        assert np.array_equal(yfull[:n].numpy(), oop.matmat(x)), name  # bitwise: fixed term order per row
+        assert np.array_equal(yfull.numpy()[pos], oop.matmat(x)), name  # bitwise: fixed term order per row
         # dot products: local partial sums all-reduced
-        part = torch.tensor([float(np.dot(x[b:e], y_local[b:e]))], dtype=torch.float64)
+        part = torch.tensor([float(np.dot(x[rows], y_rows[rows]))], dtype=torch.float64)
         dist.all_reduce(part)
         assert abs(part.item() - float(np.dot(x, oop.matmat(x)))) < 1e-9
     dist.barrier()
