@@ -8,6 +8,7 @@
 // compiled kernel with the interpreted program runs instead (same algorithm, ~2x the instructions).
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cstdlib>
@@ -241,15 +242,63 @@ bool jit_enabled() {
 }
 
 // NVRTC: generated program + matvec_kernel.cuh -> sm_100a cubin (empty on failure)
+// On-disk cache of compiled modules: $SPED_CACHE_DIR, else $XDG_CACHE_HOME/sped-b200, else
+// ~/.cache/sped-b200; the key hashes every source byte and option.  SPED_CACHE_DIR="" disables it.
+std::string cubin_cache_path(std::string const& header) {
+  char const* dir = std::getenv("SPED_CACHE_DIR");
+  std::string base;
+  if (dir) {
+    if (!*dir) return "";
+    base = dir;
+  } else if (char const* xdg = std::getenv("XDG_CACHE_HOME")) {
+    base = std::string(xdg) + "/sped-b200";
+  } else if (char const* home = std::getenv("HOME")) {
+    base = std::string(home) + "/.cache/sped-b200";
+  } else {
+    return "";
+  }
+  u64 h = 0xcbf29ce484222325ull;
+  auto mix = [&](char const* s) {
+    for (; *s; ++s) h = (h ^ (unsigned char)*s) * 0x100000001b3ull;
+    h = (h ^ 0xff) * 0x100000001b3ull;
+  };
+  mix(header.c_str());
+  mix(k_src_device_types);
+  mix(k_src_matvec_kernel);
+  mix("sm_100a c++17 lineinfo v1");
+  std::string mk = "mkdir -p '" + base + "' 2>/dev/null";
+  if (std::system(mk.c_str()) != 0) return "";
+  char name[32];
+  std::snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
+  return base + name;
+}
+
 std::vector<char> compile_cubin(Basis& b, int dtype, int nb) {
   std::vector<char> cubin;
+  std::string program = Gen(b.program).run();
+  std::string header = std::string("#define SPED_T ") + dtype_name(dtype) + "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
+  std::string cache_file = cubin_cache_path(header);
+  if (!cache_file.empty()) {
+    if (FILE* f = std::fopen(cache_file.c_str(), "rb")) {
+      std::fseek(f, 0, SEEK_END);
+      long size = std::ftell(f);
+      std::fseek(f, 0, SEEK_SET);
+      if (size > 0) {
+        cubin.resize((size_t)size);
+        if (std::fread(cubin.data(), 1, cubin.size(), f) != cubin.size()) cubin.clear();
+      }
+      std::fclose(f);
+      if (!cubin.empty()) {
+        SPED_LOG("jit: reusing %s", cache_file.c_str());
+        return cubin;
+      }
+    }
+  }
   NvrtcApi& api = nvrtc();
   if (!api.handle) {
     SPED_LOG("jit: NVRTC not available, using the interpreted-program kernel");
     return cubin;
   }
-  std::string program = Gen(b.program).run();
-  std::string header = std::string("#define SPED_T ") + dtype_name(dtype) + "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
   std::string main_src =
       "#define SPED_JIT 1\n#include \"device_types.h\"\n#include \"sped_jit_program.h\"\n#include \"matvec_kernel.cuh\"\n";
   char const* hdr_src[] = {k_src_device_types, header.c_str(), k_src_matvec_kernel};
@@ -274,6 +323,14 @@ std::vector<char> compile_cubin(Basis& b, int dtype, int nb) {
   cubin.resize(size);
   api.GetCUBIN(prog, cubin.data());
   api.DestroyProgram(&prog);
+  if (!cache_file.empty()) {  // publish atomically: several ranks may compile the same module
+    std::string tmp = cache_file + "." + std::to_string((long)getpid()) + ".tmp";
+    if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
+      bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+      ok = (std::fclose(f) == 0) && ok;
+      if (!ok || std::rename(tmp.c_str(), cache_file.c_str()) != 0) std::remove(tmp.c_str());
+    }
+  }
   if (char const* dump = std::getenv("SPED_JIT_DUMP")) {  // inspection: cuobjdump -sass <file>
     if (FILE* f = std::fopen(dump, "wb")) {
       std::fwrite(cubin.data(), 1, cubin.size(), f);

@@ -24,7 +24,7 @@ from spin_ed_b200 import decks  # noqa: E402
 def main():
     cases = {"heisenberg_chain_4": decks.load("heisenberg_chain_4"), "heisenberg_chain_10": decks.load("heisenberg_chain_10"),
              "heisenberg_kagome_12": decks.load("heisenberg_kagome_12")}
-    cases.update(extra_configs())
+    cases.update({k: v for k, v in extra_configs().items() if v["basis"]["number_spins"] <= 12})
     out = {}
     for name, cfg in cases.items():
         b = cfg["basis"]

@@ -55,6 +55,12 @@ def extra_configs():
     out["chain_10_inv_only"] = {
         "basis": {"number_spins": 10, "hamming_weight": 5, "spin_inversion": -1, "symmetries": []},
         "hamiltonian": decks.chain(10)["hamiltonian"], "observables": []}
+    # wide words: > 48 spins take the plain 64-bit path (no packed keys), 64 spins fill the word
+    out["chain_50_hw2"] = decks.chain(50, 2, None, (0, 0))
+    out["chain_64_hw2"] = decks.chain(64, 2, None, (0, 0))
+    out["chain_40_hw3_k"] = decks.chain(40, 3, None, (20, 1))
+    # spin inversion without a hamming-weight restriction
+    out["chain_10_inv_nohw"] = decks.chain(10, None, 1, (0, 0))
     # 3-site and 1-site terms with a complex matrix: chirality-like term + field
     sx = np.array([[0, 1], [1, 0]], dtype=complex); sy = np.array([[0, -1j], [1j, 0]]); sz = np.diag([1.0 + 0j, -1.0])
     def kron3(a, b, c): return np.kron(a, np.kron(b, c))

@@ -95,11 +95,12 @@ def test_compute_fails_loudly_without_gpu():
 
 
 @pytest.mark.parametrize("name", SMALL_DECKS + ["heisenberg_square_5x5", "heisenberg_pyrochlore_32", "heisenberg_square_6x6",
-                                                "heisenberg_chain_40", "heisenberg_chain_42"])
+                                                "heisenberg_chain_40", "heisenberg_chain_42", "chain_50_hw2", "chain_64_hw2",
+                                                "chain_40_hw3_k", "chain_10_inv_nohw", "chain_8_k1_complex"])
 def test_program_matches_oracle_state_info(oracle, name):
     """The compiled canonicalisation program (interpreted on the host) must give the oracle's
     representative, character and norm for random states of the sector."""
-    cfg = decks.load(name)
+    cfg = extra_configs()[name] if name in extra_configs() else decks.load(name)
     ob, _ = oracle_problem(oracle, cfg)
     if ob.group_size * (2 if ob.spin_inversion else 1) <= 1:
         pytest.skip("trivial group")
@@ -229,13 +230,14 @@ def _jit_source(basis):
 
 
 @pytest.mark.parametrize("name", ["heisenberg_chain_10", "heisenberg_square_4x4", "heisenberg_square_5x5",
-                                  "heisenberg_pyrochlore_32", "heisenberg_square_6x6", "heisenberg_chain_42"])
+                                  "heisenberg_pyrochlore_32", "heisenberg_square_6x6", "heisenberg_chain_42",
+                                  "chain_50_hw2", "chain_64_hw2", "chain_40_hw3_k", "chain_8_k1_complex"])
 def test_jit_generated_canonicalisation_matches_oracle(oracle, name, tmp_path):
     """The straight-line code handed to NVRTC, compiled for the host with g++ (funnel shift
     emulated), must canonicalise exactly like the oracle."""
     import subprocess
 
-    cfg = decks.load(name)
+    cfg = extra_configs()[name] if name in extra_configs() else decks.load(name)
     ob, _ = oracle_problem(oracle, cfg)
     uc = product_problem(cfg)
     src = _jit_source(uc.cBasis)
