@@ -64,8 +64,9 @@ def _worker(rank, world, port, ok):
 
 def test_world_size_2_sharding_logic():
     world = 2
-    ok = mp.Array("i", [0] * world)
-    procs = [mp.Process(target=_worker, args=(r, world, 29431, ok)) for r in range(world)]
+    ctx = mp.get_context("spawn")  # never fork a process that already runs OpenMP threads (the oracle)
+    ok = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_worker, args=(r, world, 29431, ok)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
