@@ -50,6 +50,9 @@ def algorithmic_bytes(n_rows, n_off, elem_size, symmetric):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (about
+    one sample per millisecond -- the timed region of a 2 ms matvec is far shorter than nvidia-smi's
+    100 ms period); `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -57,16 +60,67 @@ class ClockSampler:
     def __init__(self, device_index=0):
         self.proc = None
         self.device_index = device_index
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+        self.nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device_index])
+            except Exception:
+                pass
+        return self.device_index
+
+    def _poll(self, handle):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((sm, reasons))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
         try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.nvml = nv
+            self.thread = threading.Thread(target=self._poll, args=(handle,), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-i", str(self._physical_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            sm = [float(v) for v, _ in self.samples]
+            reasons = sorted(name for name, bit in bits.items() if any(r & bit for _, r in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.max_sm),
+                    "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -91,7 +145,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def cpu_sample_rate(O, oop, n, seconds, dtype=np.float64):
@@ -325,6 +379,35 @@ def run_ours(args):
     local_off = n_off * n_local / max(n, 1)
     alg_bytes = algorithmic_bytes(n_local, local_off, es, symmetric)
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+
+    # the same kernel with single-precision storage (what `datatype: float32` decks such as 6x6 ask
+    # for; accumulation stays f64): kernel only, reported beside the f64 headline
+    f32_leg = None
+    if is_real:
+        x32 = xfull.to(torch.float32)
+        y32 = torch.zeros(max(n_local, 1), dtype=torch.float32, device=dev)
+        tag32 = ffi.DTYPE_TAGS[np.dtype(np.float32)]
+        for _ in range(3):
+            ffi.operatorMatmatDevice(op, tag32, 1, x32.data_ptr(), chunk * world, y32.data_ptr(), max(n_local, 1),
+                                     stream.cuda_stream)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            ffi.operatorMatmatDevice(op, tag32, 1, x32.data_ptr(), chunk * world, y32.data_ptr(), max(n_local, 1),
+                                     stream.cuda_stream)
+        b.record()
+        barrier()
+        t32 = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
+        ms32 = float(t32.item())
+        bytes32 = algorithmic_bytes(n_local, local_off, 4, symmetric)
+        f32_leg = {"kernel_ms": ms32, "value": (rows + n_off) / (ms32 * 1e-3) if world == 1 else None, "unit": UNIT,
+                   "algorithmic_bytes_per_launch": bytes32, "roofline_frac_hbm": bytes32 / (ms32 * 1e-3) / 1e9 / peak,
+                   "rel_l2_vs_f64": float(((y32[:n_local].double() - ylocal[:n_local]).norm() /
+                                           ylocal[:n_local].norm().clamp_min(1e-300)).item()) if n_local else 0.0}
+        del x32, y32
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -370,6 +453,7 @@ def run_ours(args):
     extra = {"basis_build_s": build_wall, "basis_build_device_s": ffi.basisBuildSeconds(basis), "rows": rows,
              "offdiag_elements": n_off, "program": ffi.basisProgramStats(basis), "peak_source": peak_src,
              "kernel_ms": kern_ms, "kernel_ms_per_rank": kern_all, "operator_cache": cache_info,
+             "float32_storage": f32_leg, "cached_variant": os.environ.get("SPED_CACHED_VARIANT", "default"),
              "matrix_free": {"ms_per_step": matrix_free_ms, "value": (rows + n_off) / (matrix_free_ms * 1e-3),
                              "unit": UNIT, "roofline_frac_hbm": mf_achieved / peak,
                              "note": "integer-ALU bound: canonicalisation over the symmetry group per element"}}
@@ -437,7 +521,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_DECK)

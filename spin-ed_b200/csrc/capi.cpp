@@ -13,7 +13,7 @@
 
 namespace sped {
 
-bool g_logging = false;
+bool g_logging = std::getenv("SPED_LOG") != nullptr;  // also ls_enable_logging()
 std::uint64_t g_launches = 0;
 
 static thread_local int t_last_code = 0;

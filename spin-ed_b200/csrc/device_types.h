@@ -110,11 +110,13 @@ struct MatvecParams {
 // column indices with one coalesced 128-byte load per j.
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
-  u32 const* idx;        // global row index of the target representative
-  dev_u16 const* code;   // index into `table`
+  u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
+  void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
   dev_u16 const* len;    // [local rows] number of stored elements of the row
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
+  int code_wide;         // 1: u16 codes
+  u32 n_codes;           // entries of `table`
 };
 
 struct FillParams {
@@ -122,12 +124,14 @@ struct FillParams {
   TermsView terms;
   u64 const* slice_off;
   u32* idx;
-  dev_u16* code;
+  void* code;              // u8 or u16 per slot, see code_wide
   dev_u16* len;
   dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
   dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
-  u32 denom;               // number of distinct phases (1 for the trivial group)
+  dev_u16 const* pid_map;  // [denom] phase numerator -> id among the phases that occur (null: trivial group)
+  u32 denom;               // number of distinct phases that occur (1 for the trivial group)
   u32 n_sid;               // number of distinct stabiliser sizes (1 for the trivial group)
+  int code_wide;           // 1: u16 codes
   int* overflow;
 };
 

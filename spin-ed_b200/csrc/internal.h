@@ -209,7 +209,9 @@ struct Operator {
   bool cache_rejected = false;  // decided not to (or failed to) build for this basis generation
   DeviceBuffer<u64> c_slice_off;
   DeviceBuffer<u32> c_idx;
-  DeviceBuffer<std::uint16_t> c_code, c_len;
+  DeviceBuffer<unsigned char> c_code;  // u8 or u16 per slot
+  int c_code_wide = 0;
+  DeviceBuffer<std::uint16_t> c_len;
   DeviceBuffer<double> c_table;
   u64 c_slices = 0, c_slots = 0, cache_bytes = 0;
   double cache_build_seconds = 0;

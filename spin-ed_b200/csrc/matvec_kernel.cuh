@@ -240,7 +240,10 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       p.idx[base + (u64)j * 32] = (u32)dist_global_to_pos(dist, idx);  // stored ready for the gather
-      p.code[base + (u64)j * 32] = (dev_u16)((hid * p.denom + (u32)ph) * p.n_sid + sid);
+      u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
+      u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
+      if (p.code_wide) static_cast<dev_u16*>(p.code)[base + (u64)j * 32] = (dev_u16)code;
+      else static_cast<dev_u8*>(p.code)[base + (u64)j * 32] = (dev_u8)code;
       ++j;
     });
     p.len[i] = (dev_u16)j;

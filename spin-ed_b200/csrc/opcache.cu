@@ -9,8 +9,9 @@
 // coefficient is rebuilt from the same factors,  w = v * (norm_s * (1 / norm_r)).
 //
 // Layout (sliced ELL): rows in slices of 32 = one warp; element j of lane l of slice s is at
-// slice_off[s] + 32 j + l.  Column indices are u32 (N < 2^32), coefficient codes u16 into a table
-// of (Re v, Im v, norm_s), v = M[a][b] * chi(g').  6 bytes per element.
+// slice_off[s] + 32 j + l.  Column indices are u32 (N < 2^32), coefficient codes u8 (u16 when there
+// are more than 256 distinct (value, phase, stabiliser) triples) into a table of (Re v, Im v,
+// norm_s), v = M[a][b] * chi(g').  5 or 6 bytes per element.
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -88,14 +89,16 @@ __global__ void __launch_bounds__(kThreads) cache_fill_kernel(FillParams p, Prog
   }
 }
 
-// table[c] = (Re v, Im v, norm_s) for code c = (hid * denom + ph) * n_sid + sid; built on the
-// device so that v is rounded exactly like in the matrix-free kernel.
+// table[c] = (Re v, Im v, norm_s) for code c = (hid * n_pid + pid) * n_sid + sid, pid numbering the
+// phase numerators that occur in the group (pid_phase[pid]); built on the device so that v is
+// rounded exactly like in the matrix-free kernel.
 __global__ void table_kernel(double const* values_re, double const* values_im, double const* chi_table,
-                             double const* norm_table, std::uint16_t const* sid_stab, u32 n_hid, u32 denom, u32 n_sid,
-                             bool cplx, bool sym, double* table) {
+                             double const* norm_table, std::uint16_t const* sid_stab, std::uint16_t const* pid_phase,
+                             u32 n_hid, u32 n_pid, u32 n_sid, bool cplx, bool sym, double* table) {
   u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_hid * denom * n_sid) return;
-  u32 sid = c % n_sid, ph = (c / n_sid) % denom, hid = c / (n_sid * denom);
+  if (c >= n_hid * n_pid * n_sid) return;
+  u32 sid = c % n_sid, pid = (c / n_sid) % n_pid, hid = c / (n_sid * n_pid);
+  u32 ph = sym ? pid_phase[pid] : 0u;
   double2 v = make_double2(values_re[hid], values_im[hid]);
   if (sym) {
     if (cplx) {
@@ -122,28 +125,125 @@ struct CachedParams {
   int sym;
 };
 
+// ---- cache-policy loads (PTX): the (index, code) stream is read exactly once per application, so
+// it bypasses L1 and is marked evict-first in L2; the gathers of x are marked evict-last so that
+// as much of the vector as possible stays resident in the 126 MB L2 between touches.
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+template <bool HINT>
+__device__ __forceinline__ u32 load_stream(u32 const* a, u64 pol) {
+  if constexpr (HINT) {
+    u32 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+  } else {
+    return __ldg(a);
+  }
+}
+template <bool HINT>
+__device__ __forceinline__ u32 load_stream(std::uint16_t const* a, u64 pol) {
+  if constexpr (HINT) {
+    u32 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+  } else {
+    return (u32)__ldg(a);
+  }
+}
+template <bool HINT>
+__device__ __forceinline__ u32 load_stream(std::uint8_t const* a, u64 pol) {
+  if constexpr (HINT) {
+    u32 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+  } else {
+    return (u32)__ldg(a);
+  }
+}
+// gather of one vector entry as the accumulator type
+template <bool HINT> __device__ __forceinline__ double load_x(float const* a, u64 pol) {
+  if constexpr (HINT) {
+    float v;
+    asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+    return (double)v;
+  } else {
+    return (double)__ldg(a);
+  }
+}
+template <bool HINT> __device__ __forceinline__ double load_x(double const* a, u64 pol) {
+  if constexpr (HINT) {
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+    return v;
+  } else {
+    return __ldg(a);
+  }
+}
+template <bool HINT> __device__ __forceinline__ double2 load_x(float2 const* a, u64 pol) {
+  if constexpr (HINT) {
+    float x, y;
+    asm("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(x), "=f"(y) : "l"(a), "l"(pol));
+    return make_double2(x, y);
+  } else {
+    float2 v = __ldg(a);
+    return make_double2(v.x, v.y);
+  }
+}
+template <bool HINT> __device__ __forceinline__ double2 load_x(double2 const* a, u64 pol) {
+  if constexpr (HINT) {
+    double2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
+    return v;
+  } else {
+    return __ldg(a);
+  }
+}
+
 // y = H x from the cache: one warp per slice, coalesced index/code loads, read-only gathers of x,
-// accumulation in the stored (= matrix-free) order.
-template <class T, int NB>
+// accumulation in the stored (= matrix-free) order.  Elements are taken U at a time: all U index
+// and code loads are issued first, then the U gathers, then the U multiply-adds in order, so every
+// thread keeps U independent gathers in flight.
+template <class T, int NB, class Code, bool SYM, bool HINT, int U>
 __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p) {
   typedef Traits<T> TR;
   typedef typename TR::Acc Acc;
   constexpr bool CPLX = TR::cplx;
-  T const* x = static_cast<T const*>(p.x);
-  T* y = static_cast<T*>(p.y);
+  T const* __restrict__ x = static_cast<T const*>(p.x);
+  T* __restrict__ y = static_cast<T*>(p.y);
+  u32 const* __restrict__ cidx = p.cache.idx;
+  Code const* __restrict__ ccode = static_cast<Code const*>(p.cache.code);
+  double const* __restrict__ table = p.cache.table;
+  if constexpr (sizeof(Code) == 1) {  // at most 256 codes: the coefficient table lives in shared memory
+    __shared__ double s_table[3 * 256];
+    for (u32 k = threadIdx.x; k < 3 * p.cache.n_codes; k += blockDim.x) s_table[k] = p.cache.table[k];
+    __syncthreads();
+    table = s_table;
+  }
+  u64 const pol_stream = HINT ? l2_policy_evict_first() : 0;
+  u64 const pol_x = HINT ? l2_policy_evict_last() : 0;
   u64 const n_local = p.ctx.dist.n_local;
   u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;  // this rank's shard inside the replicated x
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
-    u64 const row = dist_local_to_global(p.ctx.dist, i);
     double inv_nr = 1.0;
-    if (p.sym) inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
+    if constexpr (SYM) {
+      u64 const row = dist_local_to_global(p.ctx.dist, i);
+      inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
+    }
     Acc acc[NB];
     double dre = __ldg(p.diag_re + i);
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
       acc[c] = acc_zero(Acc());
       if (c < (int)p.ncols) {
-        Acc xv = TR::load(x + (u64)c * p.xs + self0 + i);
+        Acc xv = load_x<HINT>(x + (u64)c * p.xs + self0 + i, pol_x);
         if constexpr (CPLX) {
           double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
           acc_fma(acc[c], make_double2(dre, dim_), xv);
@@ -154,28 +254,62 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
     }
     u64 const base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
     u32 const len = __ldg(p.cache.len + i);
-#pragma unroll 4
-    for (u32 j = 0; j < len; ++j) {
-      u64 const pos = base + (u64)j * 32;
-      u64 const idx = __ldg(p.cache.idx + pos);
-      double const* t = p.cache.table + 3 * (u32)__ldg(p.cache.code + pos);
-      double scale = 1.0;
-      if (p.sym) scale = __ldg(t + 2) * inv_nr;
-      if constexpr (CPLX) {
-        double2 w = make_double2(__ldg(t), __ldg(t + 1));
-        if (p.sym) {
-          w.x *= scale;
-          w.y *= scale;
+    for (u32 j0 = 0; j0 < len; j0 += U) {
+      u32 idx[U], code[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        bool const live = j0 + u < len;
+        u64 const pos = base + (u64)(j0 + u) * 32;
+        idx[u] = live ? load_stream<HINT>(cidx + pos, pol_stream) : (u32)(self0 + i);
+        code[u] = live ? load_stream<HINT>(ccode + pos, pol_stream) : 0u;
+      }
+      if constexpr (NB == 1) {
+        Acc xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = load_x<HINT>(x + idx[u], pol_x);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j0 + u < len) {
+            double const* t = table + 3 * code[u];
+            if constexpr (CPLX) {
+              double2 w = make_double2(t[0], t[1]);
+              if constexpr (SYM) {
+                double const scale = t[2] * inv_nr;
+                w.x *= scale;
+                w.y *= scale;
+              }
+              acc_fma(acc[0], w, xv[u]);
+            } else {
+              double w = t[0];
+              if constexpr (SYM) w = w * (t[2] * inv_nr);
+              acc_fma(acc[0], w, xv[u]);
+            }
+          }
         }
-#pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
       } else {
-        double w = __ldg(t);
-        if (p.sym) w = w * scale;
 #pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (c < (int)p.ncols) acc_fma(acc[c], w, TR::load(x + (u64)c * p.xs + idx));
+        for (int u = 0; u < U; ++u) {
+          if (j0 + u < len) {
+            double const* t = table + 3 * code[u];
+            if constexpr (CPLX) {
+              double2 w = make_double2(t[0], t[1]);
+              if constexpr (SYM) {
+                double const scale = t[2] * inv_nr;
+                w.x *= scale;
+                w.y *= scale;
+              }
+#pragma unroll
+              for (int c = 0; c < NB; ++c)
+                if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
+            } else {
+              double w = t[0];
+              if constexpr (SYM) w = w * (t[2] * inv_nr);
+#pragma unroll
+              for (int c = 0; c < NB; ++c)
+                if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
+            }
+          }
+        }
       }
     }
 #pragma unroll
@@ -184,10 +318,52 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
   }
 }
 
+// SPED_CACHED_VARIANT (tuning knob, default = the measured best): bit 0 cache-policy loads,
+// bit 1 eight (instead of four) elements in flight per thread; 5 = cache-policy loads, sixteen in flight.
+int cached_variant() {
+  static int v = [] {
+    char const* e = std::getenv("SPED_CACHED_VARIANT");
+    return e && *e ? std::atoi(e) : 1;
+  }();
+  return v;
+}
+
+// Persistent launch: one wave of exactly as many blocks as are resident (occupancy x 148 SMs).
+template <void (*Kernel)(CachedParams)>
+void launch_cached_kernel(CachedParams const& p, cudaStream_t s) {
+  static int const per_sm = [] {
+    int n = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, Kernel, kThreads, 0));
+    char const* e = std::getenv("SPED_CACHED_BLOCKS_PER_SM");
+    if (e && *e) n = std::min(n, std::max(1, std::atoi(e)));
+    return std::max(n, 1);
+  }();
+  int const grid = persistent_grid(p.ctx.dist.n_local, kThreads, per_sm);
+  Kernel<<<grid, kThreads, 0, s>>>(p);
+}
+
+template <class T, int NB, class Code, bool SYM>
+void launch_cached_variant(CachedParams const& p, cudaStream_t s) {
+  switch (cached_variant() & 7) {
+    case 5: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 16>>(p, s); break;
+    case 0: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 4>>(p, s); break;
+    case 1: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4>>(p, s); break;
+    case 2: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 8>>(p, s); break;
+    default: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8>>(p, s); break;
+  }
+}
+
+template <class T, int NB>
+void launch_cached_nb(CachedParams const& p, cudaStream_t s) {
+  bool const wide = p.cache.code_wide != 0, sym = p.sym != 0;
+  if (wide && sym) launch_cached_variant<T, NB, std::uint16_t, true>(p, s);
+  else if (wide) launch_cached_variant<T, NB, std::uint16_t, false>(p, s);
+  else if (sym) launch_cached_variant<T, NB, std::uint8_t, true>(p, s);
+  else launch_cached_variant<T, NB, std::uint8_t, false>(p, s);
+}
+
 template <class T>
 void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
-  u64 n_local = p.ctx.dist.n_local;
-  int grid = persistent_grid(n_local, kThreads, 8);
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
   for (u64 c0 = 0; c0 < block;) {
@@ -196,8 +372,8 @@ void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
     p.y = y + c0 * ys;
     bool wide = left > 1;
     p.ncols = (u32)std::min<u64>(left, wide ? 4 : 1);
-    if (wide) cached_matvec_kernel<T, 4><<<grid, kThreads, 0, s>>>(p);
-    else cached_matvec_kernel<T, 1><<<grid, kThreads, 0, s>>>(p);
+    if (wide) launch_cached_nb<T, 4>(p, s);
+    else launch_cached_nb<T, 1>(p, s);
     KERNEL_LAUNCHED();
     c0 += p.ncols;
   }
@@ -286,8 +462,27 @@ bool Operator::cache_usable() {
   } else {
     sid_stab.push_back(1);
   }
-  u32 const denom = sym ? (u32)b.group->denom : 1u;
-  u64 const n_codes = (u64)values_re.size() * denom * sid_stab.size();
+  // phase numerators that some element of G' carries (the canonicalisation never reports others)
+  std::vector<std::uint16_t> pid_map, pid_phase;
+  if (sym) {
+    u32 const D = (u32)b.group->denom;
+    if (D > 65535) return reject("more than 65535 distinct phases");
+    std::vector<char> occurs(D, 0);
+    for (auto const& e : b.group->elems) {
+      occurs[(u32)e.phase % D] = 1;
+      if (b.spin_inversion < 0) occurs[((u32)e.phase + D / 2) % D] = 1;
+    }
+    pid_map.assign(D, 0);
+    for (u32 ph = 0; ph < D; ++ph)
+      if (occurs[ph]) {
+        pid_map[ph] = (std::uint16_t)pid_phase.size();
+        pid_phase.push_back((std::uint16_t)ph);
+      }
+  } else {
+    pid_phase.push_back(0);
+  }
+  u32 const n_pid = (u32)pid_phase.size();
+  u64 const n_codes = (u64)values_re.size() * n_pid * sid_stab.size();
   if (n_codes > 65536) return reject("more than 65536 distinct coefficients");
 
   // slice widths from the cheap upper bound, then offsets
@@ -303,28 +498,32 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * 6 + n_local * 2 + (c_slices + 1) * 8 + n_codes * 24;
+  c_code_wide = n_codes > 256 ? 1 : 0;
+  u64 const code_bytes = c_code_wide ? 2 : 1;
+  u64 need = c_slots * (4 + code_bytes) + n_local * 2 + (c_slices + 1) * 8 + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
   if (need > free_b - free_b / 16) return reject("does not fit in device memory");
   c_idx.alloc(std::max<u64>(c_slots, 1));
-  c_code.alloc(std::max<u64>(c_slots, 1));
+  c_code.alloc(std::max<u64>(c_slots, 1) * code_bytes);
   c_len.alloc(n_local);
 
   // coefficient table
   DeviceBuffer<double> d_vre, d_vim;
-  DeviceBuffer<std::uint16_t> d_hid, d_sid_map, d_sid_stab;
+  DeviceBuffer<std::uint16_t> d_hid, d_sid_map, d_sid_stab, d_pid_map, d_pid_phase;
   d_vre.upload(values_re);
   d_vim.upload(values_im);
   d_hid.upload(hid_map);
   d_sid_map.upload(sid_map);
   d_sid_stab.upload(sid_stab);
+  d_pid_map.upload(pid_map);
+  d_pid_phase.upload(pid_phase);
   c_table.alloc(n_codes * 3);
   bool const cplx_table = !is_real();
   table_kernel<<<(unsigned)((n_codes + 127) / 128), 128>>>(d_vre.ptr, d_vim.ptr, b.d_chi_table.ptr, b.d_norm_table.ptr,
-                                                          d_sid_stab.ptr, (u32)values_re.size(), denom,
-                                                          (u32)sid_stab.size(), cplx_table, sym, c_table.ptr);
+                                                          d_sid_stab.ptr, d_pid_phase.ptr, (u32)values_re.size(),
+                                                          n_pid, (u32)sid_stab.size(), cplx_table, sym, c_table.ptr);
   KERNEL_LAUNCHED();
 
   // fill pass: the matrix-free traversal (run-time specialised kernel when available)
@@ -336,10 +535,12 @@ bool Operator::cache_usable() {
   fp.slice_off = c_slice_off.ptr;
   fp.idx = c_idx.ptr;
   fp.code = c_code.ptr;
+  fp.code_wide = c_code_wide;
   fp.len = c_len.ptr;
   fp.hid_map = d_hid.ptr;
   fp.sid_map = sym ? d_sid_map.ptr : nullptr;
-  fp.denom = denom;
+  fp.pid_map = sym ? d_pid_map.ptr : nullptr;
+  fp.denom = n_pid;
   fp.n_sid = (u32)sid_stab.size();
   fp.overflow = d_flag.ptr;
   int grid = persistent_grid(n_local, kThreads, 8);
@@ -386,10 +587,21 @@ void Operator::cached_count(unsigned long long* d_out) {
 }
 
 void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s) {
+  static bool const fetch_set = [] {  // tuning knob: DRAM->L2 fetch granularity (32, 64 or 128 bytes)
+    char const* e = std::getenv("SPED_L2_FETCH");
+    if (e && *e) {
+      cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(e));
+      size_t got = 0;
+      cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+      SPED_LOG("L2 fetch granularity: asked %s, rc %d, now %zu", e, (int)rc, got);
+    }
+    return true;
+  }();
+  (void)fetch_set;
   Basis& b = *basis;
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
-  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_table.ptr, c_slices};
+  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_table.ptr, c_slices, c_code_wide, (u32)(c_table.count / 3)};
   p.ctx = mp.ctx;
   p.diag_re = mp.diag_re;
   p.diag_im = mp.diag_im;

@@ -8,6 +8,7 @@
 // specialised one from jit.cpp, the interpreted one below is the same algorithm with the group
 // program read from shared memory.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "canon.cuh"
@@ -129,6 +130,11 @@ struct PackedTerms {
   std::vector<std::uint16_t> masks;
 };
 
+bool bond_order_descending() {
+  char const* e = std::getenv("SPED_BOND_ORDER");
+  return !(e && e[0] == '0');
+}
+
 PackedTerms pack_terms(std::vector<Interaction> const& terms) {
   PackedTerms pk;
   for (auto const& t : terms) {
@@ -154,6 +160,20 @@ PackedTerms pack_terms(std::vector<Interaction> const& terms) {
       b.zoff = (std::uint16_t)zoff;
       pk.bonds.push_back(b);
     }
+  }
+  // Bonds are visited from the most significant site down.  Rows are sorted representatives, so
+  // the 32 rows of a warp share their high bits: visiting the high bonds first keeps the lanes on
+  // the same bond -- and, when the flipped word is already canonical, on neighbouring entries of x
+  // -- for as many elements as possible (measured on a 28-site chain: 0.47 instead of 0.60
+  // 32-byte sectors per gathered element).  The order only fixes the summation order; it is the
+  // same for the matrix-free and the cached path.
+  if (bond_order_descending()) {
+    auto top = [](DevBond const& b) {
+      u32 m = 0;
+      for (u32 j = 0; j < b.k; ++j) m = std::max(m, (b.sites >> (8 * j)) & 0xffu);
+      return m;
+    };
+    std::stable_sort(pk.bonds.begin(), pk.bonds.end(), [&](DevBond const& a, DevBond const& b) { return top(a) > top(b); });
   }
   return pk;
 }

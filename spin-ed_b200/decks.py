@@ -105,6 +105,10 @@ def load(name: str) -> dict:
             stem = stem[: -len(ext)]
     if stem in _GENERATED:
         return _GENERATED[stem]()
+    if stem.startswith("heisenberg_chain_") and stem[17:].isdigit() and int(stem[17:]) % 4 == 0:
+        # size-scaling proxies of heisenberg_chain_40 (same sector and solver options), not reference files
+        n = int(stem[17:])
+        return _chain(n, n // 2, 1, (0, 0), number_vectors=1, max_primme_basis_size=3, output=f"data/{stem}.h5")
     path = os.path.join(_HERE, "decks", stem + ".json")
     if os.path.exists(path):
         with open(path) as f:
