@@ -320,13 +320,21 @@ struct Solver {
     return h;
   }
 
-  // w <- (I - V V^H) w twice, then normalise; returns the norm after projection
-  double orthonormalize(int m, T* w) {
+  // w <- (I - V V^H) w, then normalise; returns the norm after projection.  Classical
+  // Gram-Schmidt with the DGKS criterion: a unit-length w that keeps more than half of its squared
+  // norm after the first projection needs no second pass (residuals of Ritz pairs are orthogonal to
+  // the basis up to round-off, so this is the common case and saves a full sweep over V).
+  double orthonormalize(int m, T* w, bool unit_norm_input = false) {
     double t0 = now_seconds();
     for (int pass = 0; pass < 2 && m > 0; ++pass) {
-      dots(V.ptr, m, w, false, coeff.ptr);
+      auto c = dots(V.ptr, m, w, unit_norm_input, coeff.ptr);
       multi_axpy_kernel<T><<<grid, kThreads, 0, stream>>>(V.ptr, ld, m, coeff.ptr, w, n);
       KERNEL_LAUNCHED();
+      if (unit_norm_input) {
+        double removed = 0;
+        for (auto const& v : c) removed += std::norm(v);
+        if (removed < 0.5) break;
+      }
     }
     auto nn = dots(w, 1, w, true);
     double nrm = std::sqrt(std::max(0.0, nn[0].real()));
@@ -572,7 +580,7 @@ struct Solver {
           if (nn[0].real() > 0) {
             normalize_kernel<T><<<grid, kThreads, 0, stream>>>(dst, n, scal.ptr);
             KERNEL_LAUNCHED();
-            ok = orthonormalize(m, dst) > 1e-7;
+            ok = orthonormalize(m, dst, true) > 1e-7;
           }
         }
         if (!ok) append_random();

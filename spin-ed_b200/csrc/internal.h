@@ -217,7 +217,17 @@ struct Operator {
   double cache_build_seconds = 0;
   bool cache_usable();        // true once the cache is (or has just been) built
   void drop_cache();
-  void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s);
+  // local rows [row_lo, row_hi) only (row_lo a multiple of 32); y is still indexed by local row
+  void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo = 0,
+                     u64 row_hi = ~(u64)0);
+  cudaStream_t pipe_compute = nullptr, pipe_copy = nullptr;  // host-pointer entry: kernel / D2H pipeline
+  cudaEvent_t pipe_events[8] = {};
+  ~Operator() {  // may run from a GC finalizer at process exit: errors are ignored
+    for (auto e : pipe_events)
+      if (e) cudaEventDestroy(e);
+    if (pipe_compute) cudaStreamDestroy(pipe_compute);
+    if (pipe_copy) cudaStreamDestroy(pipe_copy);
+  }
   void cached_count(unsigned long long* d_out);  // adds the local element count to *d_out
   RowDist dist{};  // rows of this rank (fixed at prepare())
   bool counted = false;

@@ -123,6 +123,7 @@ struct CachedParams {
   u64 xs, ys;
   u32 ncols;
   int sym;
+  u64 row_lo, row_hi;  // local rows handled by this launch (row_lo is a multiple of 32)
 };
 
 // ---- cache-policy loads (PTX): the (index, code) stream is read exactly once per application, so
@@ -229,9 +230,8 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
   }
   u64 const pol_stream = HINT ? l2_policy_evict_first() : 0;
   u64 const pol_x = HINT ? l2_policy_evict_last() : 0;
-  u64 const n_local = p.ctx.dist.n_local;
   u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;  // this rank's shard inside the replicated x
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
+  for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.row_hi; i += (u64)gridDim.x * blockDim.x) {
     double inv_nr = 1.0;
     if constexpr (SYM) {
       u64 const row = dist_local_to_global(p.ctx.dist, i);
@@ -319,11 +319,12 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
 }
 
 // SPED_CACHED_VARIANT (tuning knob, default = the measured best): bit 0 cache-policy loads,
-// bit 1 eight (instead of four) elements in flight per thread; 5 = cache-policy loads, sixteen in flight.
+// bit 1 eight (instead of four) elements in flight per thread.  Measured on B200 (6x6, f64):
+// 0: 2.10 ms, 1: 1.90 ms, 2: 1.83 ms, 3: 1.66 ms; sixteen in flight (86 registers): 2.00 ms.
 int cached_variant() {
   static int v = [] {
     char const* e = std::getenv("SPED_CACHED_VARIANT");
-    return e && *e ? std::atoi(e) : 1;
+    return e && *e ? std::atoi(e) : 3;
   }();
   return v;
 }
@@ -338,14 +339,13 @@ void launch_cached_kernel(CachedParams const& p, cudaStream_t s) {
     if (e && *e) n = std::min(n, std::max(1, std::atoi(e)));
     return std::max(n, 1);
   }();
-  int const grid = persistent_grid(p.ctx.dist.n_local, kThreads, per_sm);
+  int const grid = persistent_grid(p.row_hi - p.row_lo, kThreads, per_sm);
   Kernel<<<grid, kThreads, 0, s>>>(p);
 }
 
 template <class T, int NB, class Code, bool SYM>
 void launch_cached_variant(CachedParams const& p, cudaStream_t s) {
-  switch (cached_variant() & 7) {
-    case 5: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 16>>(p, s); break;
+  switch (cached_variant() & 3) {
     case 0: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 4>>(p, s); break;
     case 1: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4>>(p, s); break;
     case 2: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 8>>(p, s); break;
@@ -586,7 +586,8 @@ void Operator::cached_count(unsigned long long* d_out) {
   CUDA_CHECK(cudaGetLastError());
 }
 
-void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s) {
+void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo,
+                             u64 row_hi) {
   static bool const fetch_set = [] {  // tuning knob: DRAM->L2 fetch granularity (32, 64 or 128 bytes)
     char const* e = std::getenv("SPED_L2_FETCH");
     if (e && *e) {
@@ -610,6 +611,10 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   p.xs = xs;
   p.ys = ys;
   p.sym = b.trivial() ? 0 : 1;
+  p.row_lo = row_lo;
+  p.row_hi = std::min<u64>(row_hi, dist.n_local);
+  if (p.row_lo >= p.row_hi) return;
+  if (p.row_lo & 31) fail(SPED_INTERNAL_ERROR, "row ranges of the cached matvec start at a multiple of 32");
   switch (dtype) {
     case SPED_F32: launch_cached<float>(p, block, xs, ys, s); break;
     case SPED_F64: launch_cached<double>(p, block, xs, ys, s); break;

@@ -475,6 +475,28 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   DeviceBuffer<unsigned char>&dx = stage_x, &dy = stage_y;
   CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
   if (!cm.active()) {
+    constexpr int kPipe = 8;
+    u64 const rows_per = ((size + kPipe - 1) / kPipe + 31) & ~(u64)31;
+    if (cache_usable() && block == 1 && size >= (u64)1 << 20) {
+      // steady state: the streaming kernel runs row chunk by row chunk and the device-to-host copy
+      // of a finished chunk overlaps the kernel of the next one
+      if (!pipe_compute) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_copy, cudaStreamNonBlocking));
+        for (auto& e : pipe_events) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+      for (int c = 0; c < kPipe; ++c) {
+        u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
+        if (lo >= hi) break;
+        cached_matmat(dtype, 1, dx.ptr, size, dy.ptr, size, pipe_compute, lo, hi);
+        CUDA_CHECK(cudaEventRecord(pipe_events[c], pipe_compute));
+        CUDA_CHECK(cudaStreamWaitEvent(pipe_copy, pipe_events[c], 0));
+        CUDA_CHECK(cudaMemcpyAsync(static_cast<unsigned char*>(y) + lo * es, dy.ptr + lo * es, (hi - lo) * es,
+                                   cudaMemcpyDeviceToHost, pipe_copy));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(pipe_copy));
+      return;
+    }
     matmat_device(dtype, block, dx.ptr, size, dy.ptr, size, nullptr);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy2D(y, ys * es, dy.ptr, size * es, size * es, block, cudaMemcpyDeviceToHost));
