@@ -159,6 +159,15 @@ int sped_basis_program_stats(void const* basis, unsigned* steps, unsigned* rot_o
  * cudaStream_t (NULL = default stream). */
 int sped_operator_matmat_device(void const* op, int dtype, uint64_t block_size, void const* x_full,
                                 uint64_t x_stride, void* y_local, uint64_t y_stride, void* stream);
+/* One column, row-sharded over the ranks of the communicator: x_local holds this rank's n_local
+ * entries, x_replicated is a [world * chunk] DEVICE work vector in the [rank][local] layout (left
+ * holding the gathered vector), y_local receives this rank's rows.  The NCCL all-gather of the
+ * shards runs on the library's own stream and overlaps the part of the product whose source
+ * entries this rank owns; only the remote-source part waits for it.  This is what sped_eigh does
+ * per matvec; the per-row summation order (local class, then remote class) depends on the
+ * number of ranks, so results agree across rank counts to rounding, not bitwise. */
+int sped_operator_matvec_sharded(void const* op, int dtype, void const* x_local, void* y_local, void* x_replicated,
+                                 void* stream);
 /* Number of matrix elements one application touches: rows N and off-diagonal elements E
  * (term applications with non-zero target norm); global counts. */
 int sped_operator_count_elements(void const* op, uint64_t* rows, uint64_t* offdiag);

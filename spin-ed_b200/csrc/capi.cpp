@@ -291,6 +291,12 @@ int sped_operator_matmat_device(void const* op, int dtype, uint64_t block_size, 
                                             static_cast<cudaStream_t>(stream));
   });
 }
+int sped_operator_matvec_sharded(void const* op, int dtype, void const* x_local, void* y_local, void* x_replicated,
+                                 void* stream) {
+  return guard([&] {
+    from_handle<Operator>(op)->matvec_sharded(dtype, x_local, y_local, x_replicated, static_cast<cudaStream_t>(stream));
+  });
+}
 int sped_operator_count_elements(void const* op, uint64_t* rows, uint64_t* offdiag) {
   return guard([&] {
     u64 r, e;

@@ -7,6 +7,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -84,6 +86,11 @@ void comm_init(int world, int rank, void const* id128) {
   nccl_check(api().CommInitRank(&c, world, id, rank), "ncclCommInitRank");
   g_comm.nccl = c;
   CUDA_CHECK(cudaStreamCreateWithFlags(&g_comm.stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+  CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CUDA_CHECK(cudaStreamCreateWithPriority(&g_comm.gather_stream, cudaStreamNonBlocking, prio_hi));
+  CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_ready, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_gathered, cudaEventDisableTiming));
 }
 
 void comm_finalize() {
@@ -95,6 +102,13 @@ void comm_finalize() {
     cudaStreamDestroy(g_comm.stream);
     g_comm.stream = nullptr;
   }
+  if (g_comm.gather_stream) {
+    cudaStreamDestroy(g_comm.gather_stream);
+    g_comm.gather_stream = nullptr;
+  }
+  if (g_comm.ev_ready) cudaEventDestroy(g_comm.ev_ready);
+  if (g_comm.ev_gathered) cudaEventDestroy(g_comm.ev_gathered);
+  g_comm.ev_ready = g_comm.ev_gathered = nullptr;
   g_comm.world = 1;
   g_comm.rank = 0;
 }
@@ -139,8 +153,13 @@ RowDist make_row_dist(u64 n, int world, int rank) {
   d.n = n;
   d.world = (u32)world;
   d.rank = (u32)rank;
-  u32 lb = 12;
-  while (lb > 5 && (n >> lb) < (u64)world * 64) --lb;
+  // large blocks keep the near-diagonal elements (flips of low sites that leave the word canonical)
+  // on the owning rank: at 2^16 rows about half of a chain's elements have a local source, which
+  // the streaming kernel handles while the all-gather is still in flight; >= 256 blocks per rank
+  // keep the ranks balanced
+  u32 lb = 16;
+  if (char const* e = std::getenv("SPED_LOG2_BLOCK")) lb = (u32)std::max(5, std::min(24, std::atoi(e)));
+  while (lb > 5 && (n >> lb) < (u64)world * 256) --lb;
   d.log2b = lb;
   d.chunk = 0;
   for (int r = 0; r < world; ++r) d.chunk = std::max(d.chunk, dist_rows_of(n, (u32)world, (u32)r, lb));

@@ -108,11 +108,19 @@ struct MatvecParams {
 // first matrix-free application has found them.  Rows are grouped in slices of 32 (one warp);
 // inside a slice element j of lane l sits at slice_off[s] + 32 j + l, so a warp reads its
 // column indices with one coalesced 128-byte load per j.
+//
+// With more than one rank the elements of a row are stored in two classes: first those whose
+// source entry of x is owned by this rank (available before the all-gather of the Krylov vector
+// has delivered anything), then the remote ones.  Inside a slice the local class occupies slots
+// [0, wl) and the remote class [wl, width) for every lane, so both classes are read coalesced;
+// the streaming kernel runs once per class and the local pass overlaps the all-gather.
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
   u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
-  dev_u16 const* len;    // [local rows] number of stored elements of the row
+  dev_u16 const* len;    // [local rows] stored elements of the row (two classes: the local-source ones)
+  dev_u16 const* len_remote;  // [local rows] remote-source elements; null with one class
+  u32 const* slice_wl;   // [n_slices] slots of the local class per lane; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
   int code_wide;         // 1: u16 codes
@@ -126,6 +134,10 @@ struct FillParams {
   u32* idx;
   void* code;              // u8 or u16 per slot, see code_wide
   dev_u16* len;
+  dev_u16* len_remote;     // two classes (see CacheView): remote-source count per row; else null
+  u32 const* slice_wl;     // two classes, fill pass: slots of the local class per slice; null in the count pass
+  int count_only;          // two classes, first pass: only len / len_remote are written
+  int pad0_;
   dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
   dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
   dev_u16 const* pid_map;  // [denom] phase numerator -> id among the phases that occur (null: trivial group)

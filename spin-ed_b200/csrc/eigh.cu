@@ -358,13 +358,9 @@ struct Solver {
     if (!cm.active()) {
       op.matmat_device(dtype, nb, V.ptr + (u64)j0 * ld, ld, Wm.ptr + (u64)j0 * ld, ld, stream);
     } else {
-      for (int c = 0; c < nb; ++c) {
-        T* col = xfull.ptr;
-        CUDA_CHECK(cudaMemcpyAsync(col + (u64)cm.rank * chunk, V.ptr + (u64)(j0 + c) * ld, n * sizeof(T),
-                                   cudaMemcpyDeviceToDevice, stream));
-        comm_allgather_inplace(col, chunk * sizeof(T), stream);
-        op.matmat_device(dtype, 1, col, chunk * cm.world, Wm.ptr + (u64)(j0 + c) * ld, ld, stream);
-      }
+      // per column: all-gather of the shard overlapped with the local-source pass (operator.cu)
+      for (int c = 0; c < nb; ++c)
+        op.matvec_sharded(dtype, V.ptr + (u64)(j0 + c) * ld, Wm.ptr + (u64)(j0 + c) * ld, xfull.ptr, stream);
     }
     sync();
     stats.matvecs += nb;

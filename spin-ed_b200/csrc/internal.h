@@ -123,6 +123,8 @@ struct Comm {
   int rank = 0;
   void* nccl = nullptr;  // ncclComm_t
   cudaStream_t stream = nullptr;
+  cudaStream_t gather_stream = nullptr;           // the all-gather of a sharded matvec runs here ...
+  cudaEvent_t ev_ready = nullptr, ev_gathered = nullptr;  // ... between these two events
   bool active() const { return world > 1; }
 };
 Comm& comm();
@@ -211,15 +213,20 @@ struct Operator {
   DeviceBuffer<u32> c_idx;
   DeviceBuffer<unsigned char> c_code;  // u8 or u16 per slot
   int c_code_wide = 0;
-  DeviceBuffer<std::uint16_t> c_len;
+  DeviceBuffer<std::uint16_t> c_len, c_len_remote;  // per row: stored elements (two classes: local / remote sources)
+  DeviceBuffer<u32> c_slice_wl;                     // two classes: slots of the local class per slice
   DeviceBuffer<double> c_table;
   u64 c_slices = 0, c_slots = 0, cache_bytes = 0;
   double cache_build_seconds = 0;
   bool cache_usable();        // true once the cache is (or has just been) built
   void drop_cache();
   // local rows [row_lo, row_hi) only (row_lo a multiple of 32); y is still indexed by local row
+  // phase: 0 all, 1 diagonal + local-source class, 2 += remote-source class (two-class cache, world > 1)
   void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo = 0,
-                     u64 row_hi = ~(u64)0);
+                     u64 row_hi = ~(u64)0, int phase = 0);
+  // y_local = H x for one column given only this rank's shard of x: all-gather into `xfull`
+  // ([rank][local] layout, world * chunk entries) overlapped with the local-source pass
+  void matvec_sharded(int dtype, void const* x_local, void* y_local, void* xfull, cudaStream_t s);
   cudaStream_t pipe_compute = nullptr, pipe_copy = nullptr;  // host-pointer entry: kernel / D2H pipeline
   cudaEvent_t pipe_events[8] = {};
   ~Operator() {  // may run from a GC finalizer at process exit: errors are ignored

@@ -51,6 +51,21 @@ __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, T
   }
 }
 
+// Two classes: per slice the local class takes wl = max lenL slots per lane, the remote class
+// max lenR; widths[s] = wl + wr.
+__global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len_local, std::uint16_t const* len_remote,
+                                                               u64 n_local, u32* widths, u32* slice_wl) {
+  u64 const n_padded = (n_local + 31) & ~(u64)31;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
+    u32 l = i < n_local ? len_local[i] : 0u, r = i < n_local ? len_remote[i] : 0u;
+    u32 wl = __reduce_max_sync(0xffffffffu, l), wr = __reduce_max_sync(0xffffffffu, r);
+    if ((i & 31) == 0) {
+      widths[i >> 5] = wl + wr;
+      slice_wl[i >> 5] = wl;
+    }
+  }
+}
+
 // slice_off[s] = 32 * sum_{t < s} widths[t]   (single block; slices are few millions at most)
 __global__ void __launch_bounds__(1024) slice_scan_kernel(u32 const* widths, u64* slice_off, u64 n) {
   __shared__ u64 partial[1024];
@@ -124,7 +139,11 @@ struct CachedParams {
   u32 ncols;
   int sym;
   u64 row_lo, row_hi;  // local rows handled by this launch (row_lo is a multiple of 32)
+  int phase;           // kPhaseAll, or one class of a two-class cache (CacheView)
 };
+constexpr int kPhaseAll = 0;     // diagonal + every stored element
+constexpr int kPhaseLocal = 1;   // diagonal + elements whose source this rank owns (needs no all-gather)
+constexpr int kPhaseRemote = 2;  // y += remote-source elements
 
 // ---- cache-policy loads (PTX): the (index, code) stream is read exactly once per application, so
 // it bypasses L1 and is marked evict-first in L2; the gathers of x are marked evict-last so that
@@ -231,6 +250,7 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
   u64 const pol_stream = HINT ? l2_policy_evict_first() : 0;
   u64 const pol_x = HINT ? l2_policy_evict_last() : 0;
   u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;  // this rank's shard inside the replicated x
+  bool const two = p.cache.len_remote != nullptr;
   for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.row_hi; i += (u64)gridDim.x * blockDim.x) {
     double inv_nr = 1.0;
     if constexpr (SYM) {
@@ -238,75 +258,94 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
       inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
     }
     Acc acc[NB];
-    double dre = __ldg(p.diag_re + i);
+    if (p.phase != kPhaseRemote) {  // start from the diagonal term
+      double dre = __ldg(p.diag_re + i);
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-      acc[c] = acc_zero(Acc());
-      if (c < (int)p.ncols) {
-        Acc xv = load_x<HINT>(x + (u64)c * p.xs + self0 + i, pol_x);
-        if constexpr (CPLX) {
-          double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
-          acc_fma(acc[c], make_double2(dre, dim_), xv);
-        } else {
-          acc_fma(acc[c], dre, xv);
-        }
-      }
-    }
-    u64 const base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
-    u32 const len = __ldg(p.cache.len + i);
-    for (u32 j0 = 0; j0 < len; j0 += U) {
-      u32 idx[U], code[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        bool const live = j0 + u < len;
-        u64 const pos = base + (u64)(j0 + u) * 32;
-        idx[u] = live ? load_stream<HINT>(cidx + pos, pol_stream) : (u32)(self0 + i);
-        code[u] = live ? load_stream<HINT>(ccode + pos, pol_stream) : 0u;
-      }
-      if constexpr (NB == 1) {
-        Acc xv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = load_x<HINT>(x + idx[u], pol_x);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j0 + u < len) {
-            double const* t = table + 3 * code[u];
-            if constexpr (CPLX) {
-              double2 w = make_double2(t[0], t[1]);
-              if constexpr (SYM) {
-                double const scale = t[2] * inv_nr;
-                w.x *= scale;
-                w.y *= scale;
-              }
-              acc_fma(acc[0], w, xv[u]);
-            } else {
-              double w = t[0];
-              if constexpr (SYM) w = w * (t[2] * inv_nr);
-              acc_fma(acc[0], w, xv[u]);
-            }
+      for (int c = 0; c < NB; ++c) {
+        acc[c] = acc_zero(Acc());
+        if (c < (int)p.ncols) {
+          Acc xv = load_x<HINT>(x + (u64)c * p.xs + self0 + i, pol_x);
+          if constexpr (CPLX) {
+            double dim_ = p.diag_im ? __ldg(p.diag_im + i) : 0.0;
+            acc_fma(acc[c], make_double2(dre, dim_), xv);
+          } else {
+            acc_fma(acc[c], dre, xv);
           }
         }
-      } else {
+      }
+    } else {  // continue from what the local pass stored
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        acc[c] = acc_zero(Acc());
+        if (c < (int)p.ncols) acc[c] = TR::load(y + (u64)c * p.ys + i);
+      }
+    }
+    u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
+    // the stored elements of this lane, class by class, in stored order (one copy of the loop body:
+    // a second inlined copy costs 15 registers and with them a resident block per SM)
+    u32 first = 0, len = p.phase != kPhaseRemote ? __ldg(p.cache.len + i) : 0u;
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {
+      if (seg == 1) {
+        if (!two || p.phase == kPhaseLocal) break;
+        first = __ldg(p.cache.slice_wl + (i >> 5));
+        len = __ldg(p.cache.len_remote + i);
+      }
+      u64 const base = slice_base + (u64)first * 32;
+      for (u32 j0 = 0; j0 < len; j0 += U) {
+        u32 idx[U], code[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (j0 + u < len) {
-            double const* t = table + 3 * code[u];
-            if constexpr (CPLX) {
-              double2 w = make_double2(t[0], t[1]);
-              if constexpr (SYM) {
-                double const scale = t[2] * inv_nr;
-                w.x *= scale;
-                w.y *= scale;
+          bool const live = j0 + u < len;
+          u64 const pos = base + (u64)(j0 + u) * 32;
+          idx[u] = live ? load_stream<HINT>(cidx + pos, pol_stream) : (u32)(self0 + i);
+          code[u] = live ? load_stream<HINT>(ccode + pos, pol_stream) : 0u;
+        }
+        if constexpr (NB == 1) {
+          Acc xv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) xv[u] = load_x<HINT>(x + idx[u], pol_x);  // dead slots re-read x[self]: an L1 hit
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (j0 + u < len) {
+              double const* t = table + 3 * code[u];
+              if constexpr (CPLX) {
+                double2 w = make_double2(t[0], t[1]);
+                if constexpr (SYM) {
+                  double const scale = t[2] * inv_nr;
+                  w.x *= scale;
+                  w.y *= scale;
+                }
+                acc_fma(acc[0], w, xv[u]);
+              } else {
+                double w = t[0];
+                if constexpr (SYM) w = w * (t[2] * inv_nr);
+                acc_fma(acc[0], w, xv[u]);
               }
+            }
+          }
+        } else {
 #pragma unroll
-              for (int c = 0; c < NB; ++c)
-                if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
-            } else {
-              double w = t[0];
-              if constexpr (SYM) w = w * (t[2] * inv_nr);
+          for (int u = 0; u < U; ++u) {
+            if (j0 + u < len) {
+              double const* t = table + 3 * code[u];
+              if constexpr (CPLX) {
+                double2 w = make_double2(t[0], t[1]);
+                if constexpr (SYM) {
+                  double const scale = t[2] * inv_nr;
+                  w.x *= scale;
+                  w.y *= scale;
+                }
 #pragma unroll
-              for (int c = 0; c < NB; ++c)
-                if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
+                for (int c = 0; c < NB; ++c)
+                  if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
+              } else {
+                double w = t[0];
+                if constexpr (SYM) w = w * (t[2] * inv_nr);
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                  if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
+              }
             }
           }
         }
@@ -339,8 +378,12 @@ void launch_cached_kernel(CachedParams const& p, cudaStream_t s) {
     if (e && *e) n = std::min(n, std::max(1, std::atoi(e)));
     return std::max(n, 1);
   }();
-  int const grid = persistent_grid(p.row_hi - p.row_lo, kThreads, per_sm);
-  Kernel<<<grid, kThreads, 0, s>>>(p);
+  int grid = persistent_grid(p.row_hi - p.row_lo, kThreads, per_sm);
+  // The local-source pass runs beside NCCL's all-gather kernel: short-lived blocks (four rows per
+  // thread) keep freeing SM resources, so the gather's CTAs -- launched on a higher-priority
+  // stream -- become resident at once instead of waiting for a persistent wave to drain.
+  if (p.phase == kPhaseLocal) grid = (int)std::min<u64>(((p.row_hi - p.row_lo) + 4 * kThreads - 1) / (4 * kThreads), 1u << 30);
+  Kernel<<<std::max(grid, 1), kThreads, 0, s>>>(p);
 }
 
 template <class T, int NB, class Code, bool SYM>
@@ -402,6 +445,8 @@ void Operator::drop_cache() {
   c_idx.release();
   c_code.release();
   c_len.release();
+  c_len_remote.release();
+  c_slice_wl.release();
   c_table.release();
   c_slices = c_slots = cache_bytes = 0;
 }
@@ -485,31 +530,7 @@ bool Operator::cache_usable() {
   u64 const n_codes = (u64)values_re.size() * n_pid * sid_stab.size();
   if (n_codes > 65536) return reject("more than 65536 distinct coefficients");
 
-  // slice widths from the cheap upper bound, then offsets
-  c_slices = (n_local + 31) / 32;
-  MatvecParams mp = operator_params(*this);
-  DeviceBuffer<u32> d_widths(c_slices);
-  size_t tsm = terms_smem_bytes(mp.terms, false);
-  if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-  slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
-  KERNEL_LAUNCHED();
-  c_slice_off.alloc(c_slices + 1);
-  slice_scan_kernel<<<1, 1024>>>(d_widths.ptr, c_slice_off.ptr, c_slices);
-  KERNEL_LAUNCHED();
-  CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  c_code_wide = n_codes > 256 ? 1 : 0;
-  u64 const code_bytes = c_code_wide ? 2 : 1;
-  u64 need = c_slots * (4 + code_bytes) + n_local * 2 + (c_slices + 1) * 8 + n_codes * 24;
-  size_t free_b = 0, total_b = 0;
-  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-  if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
-  if (need > free_b - free_b / 16) return reject("does not fit in device memory");
-  c_idx.alloc(std::max<u64>(c_slots, 1));
-  c_code.alloc(std::max<u64>(c_slots, 1) * code_bytes);
-  c_len.alloc(n_local);
-
-  // coefficient table
+  // maps and coefficient table
   DeviceBuffer<double> d_vre, d_vim;
   DeviceBuffer<std::uint16_t> d_hid, d_sid_map, d_sid_stab, d_pid_map, d_pid_phase;
   d_vre.upload(values_re);
@@ -526,45 +547,87 @@ bool Operator::cache_usable() {
                                                           n_pid, (u32)sid_stab.size(), cplx_table, sym, c_table.ptr);
   KERNEL_LAUNCHED();
 
-  // fill pass: the matrix-free traversal (run-time specialised kernel when available)
+  c_slices = (n_local + 31) / 32;
+  c_code_wide = n_codes > 256 ? 1 : 0;
+  u64 const code_bytes = c_code_wide ? 2 : 1;
+  bool const two = dist.world > 1;  // local-source / remote-source classes (see CacheView)
+  MatvecParams mp = operator_params(*this);
+  size_t tsm = terms_smem_bytes(mp.terms, false);
+  c_len.alloc(n_local);
+  if (two) c_len_remote.alloc(n_local);
   DeviceBuffer<int> d_flag(1);
   CUDA_CHECK(cudaMemset(d_flag.ptr, 0, sizeof(int)));
   FillParams fp{};
   fp.ctx = mp.ctx;
   fp.terms = mp.terms;
-  fp.slice_off = c_slice_off.ptr;
-  fp.idx = c_idx.ptr;
-  fp.code = c_code.ptr;
-  fp.code_wide = c_code_wide;
   fp.len = c_len.ptr;
+  fp.len_remote = two ? c_len_remote.ptr : nullptr;
   fp.hid_map = d_hid.ptr;
   fp.sid_map = sym ? d_sid_map.ptr : nullptr;
   fp.pid_map = sym ? d_pid_map.ptr : nullptr;
   fp.denom = n_pid;
   fp.n_sid = (u32)sid_stab.size();
+  fp.code_wide = c_code_wide;
   fp.overflow = d_flag.ptr;
-  int grid = persistent_grid(n_local, kThreads, 8);
-  void* jit = sym ? jit_cache_fill_kernel(b) : nullptr;
-  if (jit) {
-    void* args[] = {&fp};
-    if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(jit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    CUDA_CHECK(cudaLaunchKernel(jit, dim3(grid), dim3(kThreads), args, tsm, nullptr));
-  } else if (!sym) {
-    if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    cache_fill_kernel<u64, false><<<grid, kThreads, tsm>>>(fp, ProgramView<u64>{});
-  } else if (b.use32()) {
-    size_t psm; bool staged;
-    auto prog = program_view32(b, psm, staged);
-    if (tsm + psm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsm + psm)));
-    cache_fill_kernel<u32, true><<<grid, kThreads, tsm + psm>>>(fp, prog);
+  // the matrix-free traversal (run-time specialised kernel when available)
+  auto launch_fill = [&]() {
+    int grid = persistent_grid(n_local, kThreads, 8);
+    void* jit = sym ? jit_cache_fill_kernel(b) : nullptr;
+    if (jit) {
+      void* args[] = {&fp};
+      if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(jit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      CUDA_CHECK(cudaLaunchKernel(jit, dim3(grid), dim3(kThreads), args, tsm, nullptr));
+    } else if (!sym) {
+      if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+      cache_fill_kernel<u64, false><<<grid, kThreads, tsm>>>(fp, ProgramView<u64>{});
+    } else if (b.use32()) {
+      size_t psm; bool staged;
+      auto prog = program_view32(b, psm, staged);
+      if (tsm + psm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsm + psm)));
+      cache_fill_kernel<u32, true><<<grid, kThreads, tsm + psm>>>(fp, prog);
+    } else {
+      size_t psm; bool staged;
+      auto prog = program_view64(b, psm, staged);
+      if (tsm + psm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsm + psm)));
+      cache_fill_kernel<u64, true><<<grid, kThreads, tsm + psm>>>(fp, prog);
+    }
+    KERNEL_LAUNCHED();
+    CUDA_CHECK(cudaGetLastError());
+  };
+
+  // slice widths: one class -- the cheap upper bound (transitions with a non-zero matrix element);
+  // two classes -- exact per-class counts from a first traversal
+  DeviceBuffer<u32> d_widths(c_slices);
+  if (two) {
+    fp.count_only = 1;
+    launch_fill();
+    c_slice_wl.alloc(c_slices);
+    class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, c_len_remote.ptr, n_local,
+                                                                                 d_widths.ptr, c_slice_wl.ptr);
+    fp.count_only = 0;
+    fp.slice_wl = c_slice_wl.ptr;
   } else {
-    size_t psm; bool staged;
-    auto prog = program_view64(b, psm, staged);
-    if (tsm + psm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(cache_fill_kernel<u64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tsm + psm)));
-    cache_fill_kernel<u64, true><<<grid, kThreads, tsm + psm>>>(fp, prog);
+    if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
   }
   KERNEL_LAUNCHED();
+  c_slice_off.alloc(c_slices + 1);
+  slice_scan_kernel<<<1, 1024>>>(d_widths.ptr, c_slice_off.ptr, c_slices);
+  KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
+  u64 need = c_slots * (4 + code_bytes) + n_local * (two ? 4 : 2) + (c_slices + 1) * (two ? 12 : 8) + n_codes * 24;
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
+  if (need > free_b - free_b / 16) return reject("does not fit in device memory");
+  c_idx.alloc(std::max<u64>(c_slots, 1));
+  c_code.alloc(std::max<u64>(c_slots, 1) * code_bytes);
+
+  fp.slice_off = c_slice_off.ptr;
+  fp.idx = c_idx.ptr;
+  fp.code = c_code.ptr;
+  launch_fill();
   CUDA_CHECK(cudaDeviceSynchronize());
   int overflow = 0;
   CUDA_CHECK(cudaMemcpy(&overflow, d_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
@@ -583,11 +646,15 @@ void Operator::cached_count(unsigned long long* d_out) {
   if (!n_local) return;
   sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local, d_out);
   KERNEL_LAUNCHED();
+  if (c_len_remote.ptr) {
+    sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len_remote.ptr, n_local, d_out);
+    KERNEL_LAUNCHED();
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 
 void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo,
-                             u64 row_hi) {
+                             u64 row_hi, int phase) {
   static bool const fetch_set = [] {  // tuning knob: DRAM->L2 fetch granularity (32, 64 or 128 bytes)
     char const* e = std::getenv("SPED_L2_FETCH");
     if (e && *e) {
@@ -602,7 +669,9 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   Basis& b = *basis;
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
-  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_table.ptr, c_slices, c_code_wide, (u32)(c_table.count / 3)};
+  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_len_remote.ptr, c_slice_wl.ptr, c_table.ptr, c_slices,
+                      c_code_wide, (u32)(c_table.count / 3)};
+  p.phase = phase;
   p.ctx = mp.ctx;
   p.diag_re = mp.diag_re;
   p.diag_im = mp.diag_im;

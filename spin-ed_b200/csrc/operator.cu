@@ -130,6 +130,11 @@ struct PackedTerms {
   std::vector<std::uint16_t> masks;
 };
 
+bool overlap_enabled() {
+  char const* e = std::getenv("SPED_OVERLAP");
+  return !(e && e[0] == '0');
+}
+
 bool bond_order_descending() {
   char const* e = std::getenv("SPED_BOND_ORDER");
   return !(e && e[0] == '0');
@@ -381,6 +386,65 @@ void Operator::matmat_device(int dtype, u64 block, void const* x, u64 xs, void* 
     case SPED_C64: launch_matvec<float2>(*this, p, dtype, block, xs, ys, s); break;
     case SPED_C128: launch_matvec<double2>(*this, p, dtype, block, xs, ys, s); break;
     default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
+  }
+}
+
+// One column, multi-rank: the all-gather of the Krylov vector runs on its own stream while the
+// streaming kernel already handles the elements whose source entries this rank owns; the remote
+// class follows once the gather has landed.  (Matrix-free mode: gather, then one kernel.)
+void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, void* xfull, cudaStream_t s) {
+  prepare();
+  Comm& cm = comm();
+  size_t const es = dtype_size(dtype);
+  u64 const n_local = dist.n_local, padded = dist.chunk * dist.world;
+  unsigned char* mine = static_cast<unsigned char*>(xfull) + (u64)dist.rank * dist.chunk * es;
+  if (n_local && x_local != mine)
+    CUDA_CHECK(cudaMemcpyAsync(mine, x_local, n_local * es, cudaMemcpyDeviceToDevice, s));
+  if (!cm.active()) {
+    matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
+    return;
+  }
+  bool const overlap = n_local > 0 && cache_usable() && c_len_remote.ptr != nullptr && overlap_enabled();
+  if (!overlap) {
+    comm_allgather_inplace(xfull, dist.chunk * es, s);
+    matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
+    return;
+  }
+  // SPED_OVERLAP_TRACE=n: device times of the first n overlapped matvecs (gather, local pass, remote pass)
+  static int trace_left = [] {
+    char const* e = std::getenv("SPED_OVERLAP_TRACE");
+    return e && *e ? std::atoi(e) : 0;
+  }();
+  cudaEvent_t t[6] = {};
+  bool const trace = trace_left > 0;
+  if (trace)
+    for (auto& e : t) CUDA_CHECK(cudaEventCreate(&e));
+  CUDA_CHECK(cudaEventRecord(cm.ev_ready, s));
+  CUDA_CHECK(cudaStreamWaitEvent(cm.gather_stream, cm.ev_ready, 0));
+  if (trace) CUDA_CHECK(cudaEventRecord(t[0], cm.gather_stream));
+  comm_allgather_inplace(xfull, dist.chunk * es, cm.gather_stream);
+  CUDA_CHECK(cudaEventRecord(cm.ev_gathered, cm.gather_stream));
+  if (trace) CUDA_CHECK(cudaEventRecord(t[1], cm.gather_stream));
+  if (trace) CUDA_CHECK(cudaEventRecord(t[2], s));
+  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 1);
+  if (trace) CUDA_CHECK(cudaEventRecord(t[3], s));
+  CUDA_CHECK(cudaStreamWaitEvent(s, cm.ev_gathered, 0));
+  if (trace) CUDA_CHECK(cudaEventRecord(t[4], s));
+  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 2);
+  if (trace) {
+    CUDA_CHECK(cudaEventRecord(t[5], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    CUDA_CHECK(cudaStreamSynchronize(cm.gather_stream));
+    float gather = 0, local = 0, remote = 0, total = 0, wait = 0;
+    cudaEventElapsedTime(&gather, t[0], t[1]);
+    cudaEventElapsedTime(&local, t[2], t[3]);
+    cudaEventElapsedTime(&wait, t[3], t[4]);
+    cudaEventElapsedTime(&remote, t[4], t[5]);
+    cudaEventElapsedTime(&total, t[2], t[5]);
+    std::fprintf(stderr, "[sped] rank %d overlapped matvec: gather %.3f ms | local pass %.3f ms, wait %.3f ms, remote pass %.3f ms | total %.3f ms\n",
+                 cm.rank, gather, local, wait, remote, total);
+    for (auto e : t) cudaEventDestroy(e);
+    --trace_left;
   }
 }
 

@@ -111,6 +111,7 @@ SIGNATURES = {
     "sped_basis_state_info": (_ci, [_vp, _u64, _vp, _vp, _vp, _vp]),
     "sped_basis_program_stats": (_ci, [_vp, C.POINTER(_cu), C.POINTER(_cu), C.POINTER(_cu)]),
     "sped_operator_matmat_device": (_ci, [_vp, _ci, _u64, _vp, _u64, _vp, _u64, _vp]),
+    "sped_operator_matvec_sharded": (_ci, [_vp, _ci, _vp, _vp, _vp, _vp]),
     "sped_operator_count_elements": (_ci, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "sped_operator_diagonal": (_ci, [_vp, _vp]),
     "sped_operator_set_cache": (_ci, [_vp, _ci]),
@@ -453,6 +454,11 @@ def basisProgramStats(basis: SpinBasis):
 
 def operatorMatmatDevice(op: Operator, dtype_tag: int, block: int, x_ptr: int, x_stride: int, y_ptr: int, y_stride: int, stream: int = 0):
     checkStatus(lib().sped_operator_matmat_device(op._ptr, dtype_tag, block, x_ptr, x_stride, y_ptr, y_stride, stream))
+
+
+def operatorMatvecSharded(op: Operator, dtype_tag: int, x_local_ptr: int, y_local_ptr: int, x_replicated_ptr: int, stream: int = 0):
+    """One column from this rank's shard: all-gather (library stream) overlapped with the local-source pass."""
+    checkStatus(lib().sped_operator_matvec_sharded(op._ptr, dtype_tag, x_local_ptr, y_local_ptr, x_replicated_ptr, stream))
 
 
 def operatorCountElements(op: Operator):
