@@ -410,7 +410,9 @@ def run_ours(args):
                                            ylocal[:n_local].norm().clamp_min(1e-300)).item()) if n_local else 0.0}
         del x32, y32
     traffic = None
-    try:
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (one-GPU runs only)
+        if world > 1:
+            raise LookupError
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f).get(args.config, {}).get("dram_bytes_per_launch")
     except Exception:
