@@ -5,8 +5,9 @@ time and time-to-ground-state), with the CPU restatement timed beside it.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config DECK]
 
 A step is one application y = H x of the deck's Hamiltonian to one Krylov vector (block size 1):
-at N > 1 the step is what the solver does per matvec -- NCCL all-gather of the row-sharded vector
-followed by the kernel on the local row block.  `value` = (N_rows + E_offdiag) / t with inputs
+at N > 1 the step is what the solver does per matvec (`sped_operator_matvec_sharded`) -- NCCL
+all-gather of the row-sharded vector, overlapped with the pass over the elements whose sources the
+rank owns, then the pass over the remote-source elements.  `value` = (N_rows + E_offdiag) / t with inputs
 resident in HBM; `e2e` = the same through the reference-facing `ls_operator_matmat` with HOST
 buffers (H2D of x and D2H of y inside the timed region).  One JSON line on stdout (rank 0).
 """

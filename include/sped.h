@@ -120,8 +120,10 @@ uint64_t sped_kernel_launches(void);              /* kernels launched by this li
 
 /* Multi-GPU: one process per GPU.  Rank 0 obtains a 128-byte NCCL unique id, the host driver
  * distributes it (torch.distributed / MPI / a file), every rank calls sped_comm_init once before
- * creating bases.  Rows and representatives work are block-partitioned over ranks; the Krylov
- * vector is all-gathered each matvec and dot products are all-reduced (NCCL over NVLink). */
+ * creating bases.  Rows (and the enumeration work of ls_build) are dealt block-cyclically over the
+ * ranks (sped_row_dist below); the Krylov vector is all-gathered each matvec -- overlapped with the
+ * part of the product that needs no remote entries -- and dot products are all-reduced (NCCL over
+ * NVLink). */
 int sped_comm_unique_id(void* out_128_bytes);
 int sped_comm_init(int world_size, int rank, void const* unique_id_128_bytes);
 int sped_comm_finalize(void);
