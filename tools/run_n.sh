@@ -1,11 +1,13 @@
 #!/bin/bash
-# tools/run_n.sh N DECK TAG [bench args...]: bench.py on N GPUs of this box, JSON line to gpurun_out/TAG.json
+# tools/run_n.sh N DECK TAG [bench args...]: bench.py on N GPUs of this box, JSON line to gpurun_out/TAG.json.
+# Every run is wrapped in `timeout` (RUN_TIMEOUT seconds, default 600): a mismatched collective hangs
+# all ranks, and an unbounded hang burns N x the GPU budget.
 N=$1; DECK=$2; TAG=$3; shift 3
 mkdir -p gpurun_out
 if [ "$N" = 1 ]; then
-  python bench.py --config $DECK "$@" > gpurun_out/$TAG.json 2> gpurun_out/$TAG.err
+  timeout ${RUN_TIMEOUT:-600} python bench.py --config $DECK "$@" > gpurun_out/$TAG.json 2> gpurun_out/$TAG.err
 else
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
+  timeout ${RUN_TIMEOUT:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
     bench.py --gpus $N --config $DECK "$@" > gpurun_out/$TAG.json 2> gpurun_out/$TAG.err
 fi
 python - <<PY

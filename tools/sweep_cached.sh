@@ -8,7 +8,7 @@ shift
 for spec in "$@"; do
   IFS=: read v bo fetch <<< "$spec"
   tag=${DECK}_v${v}_b${bo}_f${fetch:-def}
-  SPED_LOG=1 SPED_CACHED_VARIANT=$v SPED_BOND_ORDER=$bo SPED_L2_FETCH=$fetch python bench.py --config $DECK --steps 30 --warmup 3 \
+  SPED_LOG=1 SPED_CACHED_VARIANT=$v SPED_BOND_ORDER=$bo SPED_L2_FETCH=$fetch timeout ${RUN_TIMEOUT:-600} python bench.py --config $DECK --steps 30 --warmup 3 \
     --no-eigh --no-cpu --e2e-host-gb 0 > gpurun_out/sweep_$tag.json 2> gpurun_out/sweep_$tag.err
   python - <<PY
 import json
