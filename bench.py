@@ -532,10 +532,22 @@ def main():
     ap.add_argument("--config", default=DEFAULT_DECK)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-host-gb", type=float, default=24.0, help="skip the host-buffer leg above this much pinned memory")
+    ap.add_argument("--watchdog-seconds", type=float, default=1500.0,
+                    help="abort the process if the whole run takes longer (a mismatched collective hangs every rank)")
     ap.add_argument("--no-eigh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.watchdog_seconds > 0:
+        import threading
+
+        def _abort():
+            log(f"bench.py: no result after {args.watchdog_seconds:.0f} s, aborting")
+            os._exit(3)
+
+        timer = threading.Timer(args.watchdog_seconds, _abort)
+        timer.daemon = True
+        timer.start()
     # exactly one JSON line on stdout: native libraries (NCCL's version banner) write to fd 1, so
     # fd 1 is pointed at stderr for the run and the result line goes to the saved descriptor
     sys.stdout.flush()
