@@ -208,6 +208,29 @@ def test_row_distribution_is_a_balanced_block_cyclic_partition():
                 assert max(counts) - min(counts) <= (1 << ffi.rowDistribution(n, world, 0).log2_block)
 
 
+def test_row_distribution_at_the_sharded_deck_sizes():
+    """chain_40 / chain_42 on 2..8 ranks: large blocks (near-diagonal elements stay on the owning
+    rank), at least 256 blocks per rank, balance within 0.1 %, and the replicated vector still
+    addressable with 32-bit positions (the operator cache stores u32 positions)."""
+    import ctypes as C
+
+    for n in (861725794, 3204236779):
+        for world in (2, 4, 8):
+            dists = [ffi.rowDistribution(n, world, r) for r in range(world)]
+            d0 = dists[0]
+            assert d0.log2_block == 16 and (n >> d0.log2_block) >= world * 256
+            counts = [d.n_local for d in dists]
+            assert sum(counts) == n and max(counts) == d0.chunk
+            assert (max(counts) - min(counts)) / max(counts) < 1e-3
+            assert d0.chunk * world < 2**32 - 1
+            rng = np.random.default_rng(n % 1000 + world)
+            for d in dists[:: max(1, world // 2)]:
+                for i in rng.integers(0, d.n_local, size=50):
+                    g = ffi.lib().sped_dist_local_to_global(C.byref(d), int(i))
+                    assert g < n and (g >> d.log2_block) % world == d.rank
+                    assert ffi.lib().sped_dist_global_to_position(C.byref(d), g) == d.rank * d.chunk + int(i)
+
+
 def test_config_defaults_and_parsing():
     # /root/reference/src/SpinED.hs:158-173
     spec = config.parseConfig(decks.load("heisenberg_chain_4"))
