@@ -538,6 +538,10 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   if (stage_y.count < need_y) stage_y.alloc(need_y);
   DeviceBuffer<unsigned char>&dx = stage_x, &dy = stage_y;
   CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
+  // from pageable memory cudaMemcpy returns once the data is staged, possibly before the last DMA into
+  // dx has finished; the kernels below run on non-blocking streams, which the legacy stream does not
+  // order -- so wait for it explicitly
+  CUDA_CHECK(cudaStreamSynchronize(nullptr));
   if (!cm.active()) {
     constexpr int kPipe = 8;
     u64 const rows_per = ((size + kPipe - 1) / kPipe + 31) & ~(u64)31;
