@@ -553,11 +553,18 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
         CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_copy, cudaStreamNonBlocking));
         for (auto& e : pipe_events) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       }
+      // all kernels are queued first: a copy into pageable memory blocks the host, and must not
+      // keep the next chunk's kernel from being launched
+      int chunks = 0;
       for (int c = 0; c < kPipe; ++c) {
         u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
         if (lo >= hi) break;
         cached_matmat(dtype, 1, dx.ptr, size, dy.ptr, size, pipe_compute, lo, hi);
         CUDA_CHECK(cudaEventRecord(pipe_events[c], pipe_compute));
+        chunks = c + 1;
+      }
+      for (int c = 0; c < chunks; ++c) {
+        u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
         CUDA_CHECK(cudaStreamWaitEvent(pipe_copy, pipe_events[c], 0));
         CUDA_CHECK(cudaMemcpyAsync(static_cast<unsigned char*>(y) + lo * es, dy.ptr + lo * es, (hi - lo) * es,
                                    cudaMemcpyDeviceToHost, pipe_copy));
