@@ -249,6 +249,10 @@ struct Operator {
   void count_elements(u64& rows, u64& offdiag);
 };
 
+// host copy of the packed terms (operator.cu): bonds in the order the kernels visit them
+void packed_terms_host(std::vector<Interaction> const& terms, std::vector<DevBond>& bonds, std::vector<double>& pool_re,
+                       std::vector<double>& pool_im, std::vector<std::uint16_t>& masks);
+
 std::shared_ptr<Interaction> make_interaction(int k, void const* matrix, unsigned count, std::uint16_t const* sites);
 std::shared_ptr<Operator> make_operator(std::shared_ptr<Basis> b, std::vector<Interaction const*> const& terms);
 
