@@ -109,23 +109,35 @@ struct MatvecParams {
 // inside a slice element j of lane l sits at slice_off[s] + 32 j + l, so a warp reads its
 // column indices with one coalesced 128-byte load per j.
 //
-// With more than one rank the elements of a row are stored in two classes: first those whose
-// source entry of x is owned by this rank (available before the all-gather of the Krylov vector
-// has delivered anything), then the remote ones.  Inside a slice the local class occupies slots
-// [0, wl) and the remote class [wl, width) for every lane, so both classes are read coalesced;
-// the streaming kernel runs once per class and the local pass overlaps the all-gather.
+// With more than one rank the elements of a row are stored in classes by where their source entry
+// of x lives: class 0 -- owned by this rank (available before the exchange of the Krylov vector
+// has delivered anything); class 1 -- owned by one of the `near` next ranks (first exchange round);
+// class 2 -- the other ranks (second round; absent when all peers fit in one round).  Inside a slice
+// class c occupies slots [start_c, start_c+1) for every lane, so every class is read coalesced; the
+// streaming kernel runs once per class, each pass overlapping the transfer the next one waits for.
+constexpr int kMaxClasses = 3;
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
   u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
-  dev_u16 const* len;    // [local rows] stored elements of the row (two classes: the local-source ones)
-  dev_u16 const* len_remote;  // [local rows] remote-source elements; null with one class
-  u32 const* slice_wl;   // [n_slices] slots of the local class per lane; null with one class
+  dev_u16 const* len;    // [n_classes][local rows] stored elements of the row per class
+  u32 const* slice_start;  // [n_slices][2] first slot of class 1 and of class 2; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
   int code_wide;         // 1: u16 codes
   u32 n_codes;           // entries of `table`
+  u32 n_classes;         // 1 (single rank), 2 or 3
+  u32 near;              // class 1 = owners rank+1 .. rank+near (mod world)
 };
+
+// class of the entry at position `pos` of the replicated vector, seen from rank d.rank
+SPED_DIST_FN u32 dist_source_class(RowDist const& d, u64 pos, u32 n_classes, u32 near) {
+  if (n_classes == 1) return 0u;
+  u32 owner = (u32)(pos / d.chunk);
+  if (owner == d.rank) return 0u;
+  u32 dd = owner > d.rank ? owner - d.rank : owner + d.world - d.rank;
+  return (n_classes == 2 || dd <= near) ? 1u : 2u;
+}
 
 struct FillParams {
   RowContext ctx;
@@ -133,11 +145,12 @@ struct FillParams {
   u64 const* slice_off;
   u32* idx;
   void* code;              // u8 or u16 per slot, see code_wide
-  dev_u16* len;
-  dev_u16* len_remote;     // two classes (see CacheView): remote-source count per row; else null
-  u32 const* slice_wl;     // two classes, fill pass: slots of the local class per slice; null in the count pass
-  int count_only;          // two classes, first pass: only len / len_remote are written
-  int pad0_;
+  dev_u16* len;            // [n_classes][local rows]
+  u32 const* slice_start;  // several classes, fill pass: [n_slices][2] (see CacheView); null otherwise
+  int count_only;          // several classes, first pass: only `len` is written
+  u32 n_classes;
+  u32 near;
+  u32 pad0_;
   dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
   dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
   dev_u16 const* pid_map;  // [denom] phase numerator -> id among the phases that occur (null: trivial group)

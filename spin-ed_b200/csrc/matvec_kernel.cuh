@@ -212,7 +212,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
 
 // Fills the operator cache: the same traversal as matvec_rows, but instead of gathering x the
 // (target index, coefficient code) of every element that exists is written to its slot.  With
-// two classes (CacheView) a first pass with count_only set sizes the classes.
+// several classes (CacheView) a first pass with count_only set sizes the classes.
 // Consecutive local rows map to consecutive lanes (blockDim and the grid stride are multiples of
 // 32), so a warp owns exactly one slice at a time.
 template <class Canon>
@@ -221,21 +221,21 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
   BasisIndex const ix = p.ctx.index;
   RowDist const dist = p.ctx.dist;
   u64 const n_local = dist.n_local;
-  bool const two = p.len_remote != nullptr;      // local-source / remote-source classes (world > 1)
   bool const count_only = p.count_only != 0;
-  u64 const self0 = (u64)dist.rank * dist.chunk;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
     u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 base = 0;
-    u32 width = 0, wl = 0;
+    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u};  // first slot of each class; start[n_classes] = width
     if (!count_only) {
       base = __ldg(p.slice_off + slice) + (i & 31);
-      width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
-      wl = two ? __ldg(p.slice_wl + slice) : width;
+      u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
+      start[1] = p.n_classes > 1 ? __ldg(p.slice_start + 2 * slice) : width;
+      start[2] = p.n_classes > 2 ? __ldg(p.slice_start + 2 * slice + 1) : width;
+      start[3] = width;
     }
-    u32 jl = 0, jr = 0;
+    u32 cnt[kMaxClasses] = {0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -243,29 +243,29 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
-      bool const local = !two || (pos - self0 < dist.chunk);
-      if (count_only) {
-        if (local) ++jl; else ++jr;
+      u32 const cls = dist_source_class(dist, pos, p.n_classes, p.near);
+      // (constant indices only: the counters stay in registers)
+      u32 const have = cls == 0 ? cnt[0] : cls == 1 ? cnt[1] : cnt[2];
+      if (cls == 0) ++cnt[0]; else if (cls == 1) ++cnt[1]; else ++cnt[2];
+      if (count_only) return;
+      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
+      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
+      if (lo + have >= hi) {
+        *p.overflow = 1;
         return;
       }
-      u32 slot;
-      if (local) {
-        if (jl >= wl) { *p.overflow = 1; return; }
-        slot = jl++;
-      } else {
-        if (wl + jr >= width) { *p.overflow = 1; return; }
-        slot = wl + jr++;
-      }
+      u64 const at = base + (u64)(lo + have) * 32;
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
       u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
-      p.idx[base + (u64)slot * 32] = (u32)pos;
-      if (p.code_wide) static_cast<dev_u16*>(p.code)[base + (u64)slot * 32] = (dev_u16)code;
-      else static_cast<dev_u8*>(p.code)[base + (u64)slot * 32] = (dev_u8)code;
+      p.idx[at] = (u32)pos;
+      if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
+      else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
     });
-    p.len[i] = (dev_u16)jl;
-    if (two) p.len_remote[i] = (dev_u16)jr;
+    p.len[i] = (dev_u16)cnt[0];
+    if (p.n_classes > 1) p.len[n_local + i] = (dev_u16)cnt[1];
+    if (p.n_classes > 2) p.len[2 * n_local + i] = (dev_u16)cnt[2];
   }
 }
 

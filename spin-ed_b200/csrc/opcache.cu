@@ -51,17 +51,22 @@ __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, T
   }
 }
 
-// Two classes: per slice the local class takes wl = max lenL slots per lane, the remote class
-// max lenR; widths[s] = wl + wr.
-__global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len_local, std::uint16_t const* len_remote,
-                                                               u64 n_local, u32* widths, u32* slice_wl) {
+// Several classes: per slice class c takes max_lanes len_c slots per lane; widths[s] is their sum
+// and slice_start[s] = (first slot of class 1, first slot of class 2).
+__global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len, u64 n_local, u32 n_classes,
+                                                               u32* widths, u32* slice_start) {
   u64 const n_padded = (n_local + 31) & ~(u64)31;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
-    u32 l = i < n_local ? len_local[i] : 0u, r = i < n_local ? len_remote[i] : 0u;
-    u32 wl = __reduce_max_sync(0xffffffffu, l), wr = __reduce_max_sync(0xffffffffu, r);
+    u32 w[kMaxClasses] = {0u, 0u, 0u};
+#pragma unroll
+    for (u32 c = 0; c < (u32)kMaxClasses; ++c) {
+      u32 v = (c < n_classes && i < n_local) ? len[(u64)c * n_local + i] : 0u;
+      w[c] = __reduce_max_sync(0xffffffffu, v);
+    }
     if ((i & 31) == 0) {
-      widths[i >> 5] = wl + wr;
-      slice_wl[i >> 5] = wl;
+      widths[i >> 5] = w[0] + w[1] + w[2];
+      slice_start[2 * (i >> 5)] = w[0];
+      slice_start[2 * (i >> 5) + 1] = w[0] + w[1];
     }
   }
 }
@@ -139,11 +144,11 @@ struct CachedParams {
   u32 ncols;
   int sym;
   u64 row_lo, row_hi;  // local rows handled by this launch (row_lo is a multiple of 32)
-  int phase;           // kPhaseAll, or one class of a two-class cache (CacheView)
+  int beside_transfer; // this pass overlaps an exchange round (see launch_cached_kernel)
+  int phase;           // kPhaseAll, or 1 + class (CacheView): class 0 starts from the diagonal, later classes add to y
 };
 constexpr int kPhaseAll = 0;     // diagonal + every stored element
-constexpr int kPhaseLocal = 1;   // diagonal + elements whose source this rank owns (needs no all-gather)
-constexpr int kPhaseRemote = 2;  // y += remote-source elements
+constexpr int kPhaseLocal = 1;   // diagonal + elements whose source this rank owns (needs no exchange)
 
 // ---- cache-policy loads (PTX): the (index, code) stream is read exactly once per application, so
 // it bypasses L1 and is marked evict-first in L2; the gathers of x are marked evict-last so that
@@ -250,7 +255,9 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
   u64 const pol_stream = HINT ? l2_policy_evict_first() : 0;
   u64 const pol_x = HINT ? l2_policy_evict_last() : 0;
   u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;  // this rank's shard inside the replicated x
-  bool const two = p.cache.len_remote != nullptr;
+  u64 const n_rows = p.ctx.dist.n_local;
+  u32 const seg_lo = p.phase == kPhaseAll ? 0u : (u32)p.phase - 1u;           // classes handled by this launch
+  u32 const seg_hi = p.phase == kPhaseAll ? p.cache.n_classes : (u32)p.phase;
   for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.row_hi; i += (u64)gridDim.x * blockDim.x) {
     double inv_nr = 1.0;
     if constexpr (SYM) {
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
       inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
     }
     Acc acc[NB];
-    if (p.phase != kPhaseRemote) {  // start from the diagonal term
+    if (seg_lo == 0) {  // start from the diagonal term
       double dre = __ldg(p.diag_re + i);
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
           }
         }
       }
-    } else {  // continue from what the local pass stored
+    } else {  // continue from what the passes over the earlier classes stored
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
         acc[c] = acc_zero(Acc());
@@ -283,14 +290,10 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
     u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
     // the stored elements of this lane, class by class, in stored order (one copy of the loop body:
     // a second inlined copy costs 15 registers and with them a resident block per SM)
-    u32 first = 0, len = p.phase != kPhaseRemote ? __ldg(p.cache.len + i) : 0u;
 #pragma unroll 1
-    for (int seg = 0; seg < 2; ++seg) {
-      if (seg == 1) {
-        if (!two || p.phase == kPhaseLocal) break;
-        first = __ldg(p.cache.slice_wl + (i >> 5));
-        len = __ldg(p.cache.len_remote + i);
-      }
+    for (u32 seg = seg_lo; seg < seg_hi; ++seg) {
+      u32 const first = seg == 0 ? 0u : __ldg(p.cache.slice_start + 2 * (i >> 5) + (seg - 1));
+      u32 const len = __ldg(p.cache.len + (u64)seg * n_rows + i);
       u64 const base = slice_base + (u64)first * 32;
       for (u32 j0 = 0; j0 < len; j0 += U) {
         u32 idx[U], code[U];
@@ -379,10 +382,10 @@ void launch_cached_kernel(CachedParams const& p, cudaStream_t s) {
     return std::max(n, 1);
   }();
   int grid = persistent_grid(p.row_hi - p.row_lo, kThreads, per_sm);
-  // The local-source pass runs beside NCCL's all-gather kernel: short-lived blocks (four rows per
-  // thread) keep freeing SM resources, so the gather's CTAs -- launched on a higher-priority
+  // A pass that runs beside one of NCCL's transfer kernels uses short-lived blocks (four rows per
+  // thread): they keep freeing SM resources, so the transfer's CTAs -- launched on a higher-priority
   // stream -- become resident at once instead of waiting for a persistent wave to drain.
-  if (p.phase == kPhaseLocal) grid = (int)std::min<u64>(((p.row_hi - p.row_lo) + 4 * kThreads - 1) / (4 * kThreads), 1u << 30);
+  if (p.beside_transfer) grid = (int)std::min<u64>(((p.row_hi - p.row_lo) + 4 * kThreads - 1) / (4 * kThreads), 1u << 30);
   Kernel<<<std::max(grid, 1), kThreads, 0, s>>>(p);
 }
 
@@ -430,6 +433,12 @@ __global__ void __launch_bounds__(kThreads) sum_len_kernel(std::uint16_t const* 
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
 }
 
+// SPED_REMOTE_GROUPS=1: one exchange (NCCL all-gather) and one remote class even with more than two ranks
+int remote_groups() {
+  char const* e = std::getenv("SPED_REMOTE_GROUPS");
+  return e && e[0] == '1' ? 1 : 2;
+}
+
 int env_cache_mode() {
   char const* e = std::getenv("SPED_OPERATOR_CACHE");
   if (!e || !*e) return -1;
@@ -445,8 +454,9 @@ void Operator::drop_cache() {
   c_idx.release();
   c_code.release();
   c_len.release();
-  c_len_remote.release();
-  c_slice_wl.release();
+  c_slice_start.release();
+  c_classes = 1;
+  c_near = 0;
   c_table.release();
   c_slices = c_slots = cache_bytes = 0;
 }
@@ -550,18 +560,22 @@ bool Operator::cache_usable() {
   c_slices = (n_local + 31) / 32;
   c_code_wide = n_codes > 256 ? 1 : 0;
   u64 const code_bytes = c_code_wide ? 2 : 1;
-  bool const two = dist.world > 1;  // local-source / remote-source classes (see CacheView)
+  // source classes (see CacheView): local / peers of the first exchange round / of the second
+  u32 const world = dist.world;
+  c_classes = world == 1 ? 1 : (world == 2 || remote_groups() == 1) ? 2 : 3;
+  c_near = c_classes == 3 ? world / 2 : world - 1;  // 8 ranks: 4 peers in the first round, 3 in the second
+  bool const two = c_classes > 1;
   MatvecParams mp = operator_params(*this);
   size_t tsm = terms_smem_bytes(mp.terms, false);
-  c_len.alloc(n_local);
-  if (two) c_len_remote.alloc(n_local);
+  c_len.alloc(n_local * c_classes);
   DeviceBuffer<int> d_flag(1);
   CUDA_CHECK(cudaMemset(d_flag.ptr, 0, sizeof(int)));
   FillParams fp{};
   fp.ctx = mp.ctx;
   fp.terms = mp.terms;
   fp.len = c_len.ptr;
-  fp.len_remote = two ? c_len_remote.ptr : nullptr;
+  fp.n_classes = c_classes;
+  fp.near = c_near;
   fp.hid_map = d_hid.ptr;
   fp.sid_map = sym ? d_sid_map.ptr : nullptr;
   fp.pid_map = sym ? d_pid_map.ptr : nullptr;
@@ -601,11 +615,11 @@ bool Operator::cache_usable() {
   if (two) {
     fp.count_only = 1;
     launch_fill();
-    c_slice_wl.alloc(c_slices);
-    class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, c_len_remote.ptr, n_local,
-                                                                                 d_widths.ptr, c_slice_wl.ptr);
+    c_slice_start.alloc(c_slices * 2);
+    class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, d_widths.ptr,
+                                                                                 c_slice_start.ptr);
     fp.count_only = 0;
-    fp.slice_wl = c_slice_wl.ptr;
+    fp.slice_start = c_slice_start.ptr;
   } else {
     if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
     slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
@@ -616,7 +630,7 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * (4 + code_bytes) + n_local * (two ? 4 : 2) + (c_slices + 1) * (two ? 12 : 8) + n_codes * 24;
+  u64 need = c_slots * (4 + code_bytes) + n_local * 2 * c_classes + (c_slices + 1) * (two ? 16 : 8) + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
@@ -644,17 +658,13 @@ bool Operator::cache_usable() {
 void Operator::cached_count(unsigned long long* d_out) {
   u64 n_local = dist.n_local;
   if (!n_local) return;
-  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local, d_out);
+  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local * c_classes, d_out);
   KERNEL_LAUNCHED();
-  if (c_len_remote.ptr) {
-    sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len_remote.ptr, n_local, d_out);
-    KERNEL_LAUNCHED();
-  }
   CUDA_CHECK(cudaGetLastError());
 }
 
 void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo,
-                             u64 row_hi, int phase) {
+                             u64 row_hi, int phase, bool beside_transfer) {
   static bool const fetch_set = [] {  // tuning knob: DRAM->L2 fetch granularity (32, 64 or 128 bytes)
     char const* e = std::getenv("SPED_L2_FETCH");
     if (e && *e) {
@@ -669,9 +679,10 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   Basis& b = *basis;
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
-  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_len_remote.ptr, c_slice_wl.ptr, c_table.ptr, c_slices,
-                      c_code_wide, (u32)(c_table.count / 3)};
+  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_slice_start.ptr, c_table.ptr, c_slices,
+                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near};
   p.phase = phase;
+  p.beside_transfer = beside_transfer ? 1 : 0;
   p.ctx = mp.ctx;
   p.diag_re = mp.diag_re;
   p.diag_im = mp.diag_im;

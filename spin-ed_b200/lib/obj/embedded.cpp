@@ -111,23 +111,35 @@ struct MatvecParams {
 // inside a slice element j of lane l sits at slice_off[s] + 32 j + l, so a warp reads its
 // column indices with one coalesced 128-byte load per j.
 //
-// With more than one rank the elements of a row are stored in two classes: first those whose
-// source entry of x is owned by this rank (available before the all-gather of the Krylov vector
-// has delivered anything), then the remote ones.  Inside a slice the local class occupies slots
-// [0, wl) and the remote class [wl, width) for every lane, so both classes are read coalesced;
-// the streaming kernel runs once per class and the local pass overlaps the all-gather.
+// With more than one rank the elements of a row are stored in classes by where their source entry
+// of x lives: class 0 -- owned by this rank (available before the exchange of the Krylov vector
+// has delivered anything); class 1 -- owned by one of the `near` next ranks (first exchange round);
+// class 2 -- the other ranks (second round; absent when all peers fit in one round).  Inside a slice
+// class c occupies slots [start_c, start_c+1) for every lane, so every class is read coalesced; the
+// streaming kernel runs once per class, each pass overlapping the transfer the next one waits for.
+constexpr int kMaxClasses = 3;
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
   u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
-  dev_u16 const* len;    // [local rows] stored elements of the row (two classes: the local-source ones)
-  dev_u16 const* len_remote;  // [local rows] remote-source elements; null with one class
-  u32 const* slice_wl;   // [n_slices] slots of the local class per lane; null with one class
+  dev_u16 const* len;    // [n_classes][local rows] stored elements of the row per class
+  u32 const* slice_start;  // [n_slices][2] first slot of class 1 and of class 2; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
   int code_wide;         // 1: u16 codes
   u32 n_codes;           // entries of `table`
+  u32 n_classes;         // 1 (single rank), 2 or 3
+  u32 near;              // class 1 = owners rank+1 .. rank+near (mod world)
 };
+
+// class of the entry at position `pos` of the replicated vector, seen from rank d.rank
+SPED_DIST_FN u32 dist_source_class(RowDist const& d, u64 pos, u32 n_classes, u32 near) {
+  if (n_classes == 1) return 0u;
+  u32 owner = (u32)(pos / d.chunk);
+  if (owner == d.rank) return 0u;
+  u32 dd = owner > d.rank ? owner - d.rank : owner + d.world - d.rank;
+  return (n_classes == 2 || dd <= near) ? 1u : 2u;
+}
 
 struct FillParams {
   RowContext ctx;
@@ -135,11 +147,12 @@ struct FillParams {
   u64 const* slice_off;
   u32* idx;
   void* code;              // u8 or u16 per slot, see code_wide
-  dev_u16* len;
-  dev_u16* len_remote;     // two classes (see CacheView): remote-source count per row; else null
-  u32 const* slice_wl;     // two classes, fill pass: slots of the local class per slice; null in the count pass
-  int count_only;          // two classes, first pass: only len / len_remote are written
-  int pad0_;
+  dev_u16* len;            // [n_classes][local rows]
+  u32 const* slice_start;  // several classes, fill pass: [n_slices][2] (see CacheView); null otherwise
+  int count_only;          // several classes, first pass: only `len` is written
+  u32 n_classes;
+  u32 near;
+  u32 pad0_;
   dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
   dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
   dev_u16 const* pid_map;  // [denom] phase numerator -> id among the phases that occur (null: trivial group)
@@ -366,7 +379,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
 
 // Fills the operator cache: the same traversal as matvec_rows, but instead of gathering x the
 // (target index, coefficient code) of every element that exists is written to its slot.  With
-// two classes (CacheView) a first pass with count_only set sizes the classes.
+// several classes (CacheView) a first pass with count_only set sizes the classes.
 // Consecutive local rows map to consecutive lanes (blockDim and the grid stride are multiples of
 // 32), so a warp owns exactly one slice at a time.
 template <class Canon>
@@ -375,21 +388,21 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
   BasisIndex const ix = p.ctx.index;
   RowDist const dist = p.ctx.dist;
   u64 const n_local = dist.n_local;
-  bool const two = p.len_remote != nullptr;      // local-source / remote-source classes (world > 1)
   bool const count_only = p.count_only != 0;
-  u64 const self0 = (u64)dist.rank * dist.chunk;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
     u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 base = 0;
-    u32 width = 0, wl = 0;
+    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u};  // first slot of each class; start[n_classes] = width
     if (!count_only) {
       base = __ldg(p.slice_off + slice) + (i & 31);
-      width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
-      wl = two ? __ldg(p.slice_wl + slice) : width;
+      u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
+      start[1] = p.n_classes > 1 ? __ldg(p.slice_start + 2 * slice) : width;
+      start[2] = p.n_classes > 2 ? __ldg(p.slice_start + 2 * slice + 1) : width;
+      start[3] = width;
     }
-    u32 jl = 0, jr = 0;
+    u32 cnt[kMaxClasses] = {0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -397,29 +410,29 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
-      bool const local = !two || (pos - self0 < dist.chunk);
-      if (count_only) {
-        if (local) ++jl; else ++jr;
+      u32 const cls = dist_source_class(dist, pos, p.n_classes, p.near);
+      // (constant indices only: the counters stay in registers)
+      u32 const have = cls == 0 ? cnt[0] : cls == 1 ? cnt[1] : cnt[2];
+      if (cls == 0) ++cnt[0]; else if (cls == 1) ++cnt[1]; else ++cnt[2];
+      if (count_only) return;
+      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
+      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
+      if (lo + have >= hi) {
+        *p.overflow = 1;
         return;
       }
-      u32 slot;
-      if (local) {
-        if (jl >= wl) { *p.overflow = 1; return; }
-        slot = jl++;
-      } else {
-        if (wl + jr >= width) { *p.overflow = 1; return; }
-        slot = wl + jr++;
-      }
+      u64 const at = base + (u64)(lo + have) * 32;
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
       u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
-      p.idx[base + (u64)slot * 32] = (u32)pos;
-      if (p.code_wide) static_cast<dev_u16*>(p.code)[base + (u64)slot * 32] = (dev_u16)code;
-      else static_cast<dev_u8*>(p.code)[base + (u64)slot * 32] = (dev_u8)code;
+      p.idx[at] = (u32)pos;
+      if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
+      else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
     });
-    p.len[i] = (dev_u16)jl;
-    if (two) p.len_remote[i] = (dev_u16)jr;
+    p.len[i] = (dev_u16)cnt[0];
+    if (p.n_classes > 1) p.len[n_local + i] = (dev_u16)cnt[1];
+    if (p.n_classes > 2) p.len[2 * n_local + i] = (dev_u16)cnt[2];
   }
 }
 
