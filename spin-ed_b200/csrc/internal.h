@@ -254,6 +254,8 @@ struct Operator {
   void count_elements(u64& rows, u64& offdiag);
 };
 
+int exchange_rounds(unsigned world);  // opcache.cu
+
 std::shared_ptr<Interaction> make_interaction(int k, void const* matrix, unsigned count, std::uint16_t const* sites);
 std::shared_ptr<Operator> make_operator(std::shared_ptr<Basis> b, std::vector<Interaction const*> const& terms);
 

@@ -433,12 +433,6 @@ __global__ void __launch_bounds__(kThreads) sum_len_kernel(std::uint16_t const* 
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
 }
 
-// SPED_REMOTE_GROUPS=1: one exchange (NCCL all-gather) and one remote class even with more than two ranks
-int remote_groups() {
-  char const* e = std::getenv("SPED_REMOTE_GROUPS");
-  return e && e[0] == '1' ? 1 : 2;
-}
-
 int env_cache_mode() {
   char const* e = std::getenv("SPED_OPERATOR_CACHE");
   if (!e || !*e) return -1;
@@ -446,6 +440,15 @@ int env_cache_mode() {
 }
 
 }  // namespace
+
+// Number of exchange rounds of a sharded matvec (and remote source classes of the cache): a function
+// of the world size and the environment only, so that every rank makes the same choice.
+// SPED_REMOTE_GROUPS=1: one round (NCCL all-gather) even with more than two ranks.
+int exchange_rounds(unsigned world) {
+  if (world <= 1) return 0;
+  char const* e = std::getenv("SPED_REMOTE_GROUPS");
+  return (world == 2 || (e && e[0] == '1')) ? 1 : 2;
+}
 
 void Operator::drop_cache() {
   cache_ready = false;
@@ -562,7 +565,7 @@ bool Operator::cache_usable() {
   u64 const code_bytes = c_code_wide ? 2 : 1;
   // source classes (see CacheView): local / peers of the first exchange round / of the second
   u32 const world = dist.world;
-  c_classes = world == 1 ? 1 : (world == 2 || remote_groups() == 1) ? 2 : 3;
+  c_classes = world == 1 ? 1 : 1 + (u32)exchange_rounds(world);
   c_near = c_classes == 3 ? world / 2 : world - 1;  // 8 ranks: 4 peers in the first round, 3 in the second
   bool const two = c_classes > 1;
   MatvecParams mp = operator_params(*this);

@@ -404,12 +404,15 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
     matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
     return;
   }
-  bool const overlap = n_local > 0 && cache_usable() && c_classes > 1 && overlap_enabled();
-  if (!overlap) {
+  // Which collectives run must not depend on anything rank-local (a rank without rows, or one whose
+  // cache did not fit, still has to take part in the same exchange): only on world and environment.
+  if (!overlap_enabled()) {
     comm_allgather_inplace(xfull, dist.chunk * es, s);
     matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
     return;
   }
+  bool const rounds = exchange_rounds(dist.world) == 2;
+  bool const cached = n_local > 0 && cache_usable() && c_classes == (rounds ? 3u : 2u);
   // SPED_OVERLAP_TRACE=n: device times of the first n overlapped matvecs
   static int trace_left = [] {
     char const* e = std::getenv("SPED_OVERLAP_TRACE");
@@ -423,7 +426,6 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
     if (trace) CUDA_CHECK(cudaEventRecord(t[k], st));
   };
   cudaStream_t const g = cm.gather_stream;
-  bool const rounds = c_classes == 3;
   // exchange: one all-gather, or two rounds of peer groups (near ranks first)
   CUDA_CHECK(cudaEventRecord(cm.ev_ready, s));
   CUDA_CHECK(cudaStreamWaitEvent(g, cm.ev_ready, 0));
@@ -439,6 +441,15 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
   }
   CUDA_CHECK(cudaEventRecord(cm.ev_gathered, g));
   mark(2, g);
+  if (!cached) {  // no rows, or matrix-free mode: wait for the whole vector, one kernel
+    CUDA_CHECK(cudaStreamWaitEvent(s, cm.ev_gathered, 0));
+    if (n_local) matmat_device(dtype, 1, xfull, padded, y_local, n_local, s);
+    if (trace) {
+      for (auto e : t) cudaEventDestroy(e);
+      --trace_left;
+    }
+    return;
+  }
   // product: the pass over class c runs beside the transfer that class c + 1 waits for
   mark(3, s);
   cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 1, true);
