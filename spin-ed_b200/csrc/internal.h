@@ -208,6 +208,7 @@ struct Operator {
   DeviceBuffer<unsigned char> d_terms;  // packed bonds + matrices (see operator.cu)
   DeviceBuffer<double> d_diag;          // local rows (real part) [+ imaginary part if !real_diagonal]
   DeviceBuffer<unsigned char> stage_x, stage_y;  // grow-only device staging of the host-pointer entry
+  DeviceBuffer<unsigned char> block_x;           // grow-only: interleaved copy of a block of vectors (opcache.cu)
 
   // operator cache (opcache.cu): off-diagonal elements of the local rows resident in HBM
   int cache_mode = -1;        // -1: auto (build when it fits), 0: never, 1: always try

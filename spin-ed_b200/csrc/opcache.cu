@@ -360,6 +360,151 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
   }
 }
 
+// ---- block applications (ncols > 1) ----------------------------------------------------------
+// The gathers, not the bytes, bound the streaming kernel, so a block of vectors is first
+// interleaved ([position][column], NB = 2 or 4 columns, missing ones zero): the 16- or 32-byte
+// vector load that fetches an element's source for one column then brings the other columns with
+// it, and the index/code stream is read once for the whole block.
+template <class T, int NB>
+__global__ void __launch_bounds__(kThreads) interleave_kernel(T const* x, u64 xs, u32 ncols, u64 n, T* out) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      T v{};
+      if (c < (int)ncols) v = x[(u64)c * xs + i];
+      out[i * NB + c] = v;
+    }
+  }
+}
+
+// NB consecutive entries of the interleaved block as accumulator values.  `volatile`: the compiler
+// must not sink these loads into the per-element conditionals (that would serialise the gathers).
+template <int NB>
+__device__ __forceinline__ void load_xrow(double const* a, u64 pol, double (&out)[NB]) {
+#pragma unroll
+  for (int k = 0; k < NB; k += 2)
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(out[k]), "=d"(out[k + 1]) : "l"(a + k), "l"(pol));
+}
+template <int NB>
+__device__ __forceinline__ void load_xrow(float const* a, u64 pol, double (&out)[NB]) {
+  if constexpr (NB == 4) {
+    float v0, v1, v2, v3;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "l"(a), "l"(pol));
+    out[0] = v0; out[1] = v1; out[2] = v2; out[3] = v3;
+  } else {
+    float v0, v1;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v0), "=f"(v1) : "l"(a), "l"(pol));
+    out[0] = v0; out[1] = v1;
+  }
+}
+template <int NB>
+__device__ __forceinline__ void load_xrow(float2 const* a, u64 pol, double2 (&out)[NB]) {
+#pragma unroll
+  for (int k = 0; k < NB; k += 2) {
+    float v0, v1, v2, v3;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "l"(a + k), "l"(pol));
+    out[k] = make_double2(v0, v1);
+    out[k + 1] = make_double2(v2, v3);
+  }
+}
+template <int NB>
+__device__ __forceinline__ void load_xrow(double2 const* a, u64 pol, double2 (&out)[NB]) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(out[k].x), "=d"(out[k].y) : "l"(a + k), "l"(pol));
+}
+
+template <class T, int NB, class Code, bool SYM, int U>
+__global__ void __launch_bounds__(kThreads) cached_block_kernel(CachedParams p) {
+  typedef Traits<T> TR;
+  typedef typename TR::Acc Acc;
+  constexpr bool CPLX = TR::cplx;
+  T const* __restrict__ xt = static_cast<T const*>(p.x);  // interleaved: entry (pos, c) at pos * NB + c
+  T* __restrict__ y = static_cast<T*>(p.y);
+  u32 const* __restrict__ cidx = p.cache.idx;
+  Code const* __restrict__ ccode = static_cast<Code const*>(p.cache.code);
+  double const* __restrict__ table = p.cache.table;
+  if constexpr (sizeof(Code) == 1) {
+    __shared__ double s_table[3 * 256];
+    for (u32 k = threadIdx.x; k < 3 * p.cache.n_codes; k += blockDim.x) s_table[k] = p.cache.table[k];
+    __syncthreads();
+    table = s_table;
+  }
+  u64 const pol_stream = l2_policy_evict_first();
+  u64 const pol_x = l2_policy_evict_last();
+  u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;
+  u64 const n_rows = p.ctx.dist.n_local;
+  for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.row_hi; i += (u64)gridDim.x * blockDim.x) {
+    double inv_nr = 1.0;
+    if constexpr (SYM) {
+      u64 const row = dist_local_to_global(p.ctx.dist, i);
+      inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
+    }
+    Acc acc[NB];
+    {
+      Acc xv[NB];
+      load_xrow<NB>(xt + (self0 + i) * NB, pol_x, xv);
+      double const dre = __ldg(p.diag_re + i);
+      double const dim_ = (CPLX && p.diag_im) ? __ldg(p.diag_im + i) : 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        acc[c] = acc_zero(Acc());
+        if constexpr (CPLX) acc_fma(acc[c], make_double2(dre, dim_), xv[c]);
+        else acc_fma(acc[c], dre, xv[c]);
+      }
+    }
+    u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
+#pragma unroll 1
+    for (u32 seg = 0; seg < p.cache.n_classes; ++seg) {
+      u32 const first = seg == 0 ? 0u : __ldg(p.cache.slice_start + 2 * (i >> 5) + (seg - 1));
+      u32 const len = __ldg(p.cache.len + (u64)seg * n_rows + i);
+      u64 const base = slice_base + (u64)first * 32;
+      for (u32 j0 = 0; j0 < len; j0 += U) {
+        u32 idx[U], code[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          bool const live = j0 + u < len;
+          u64 const pos = base + (u64)(j0 + u) * 32;
+          idx[u] = live ? load_stream<true>(cidx + pos, pol_stream) : (u32)(self0 + i);
+          code[u] = live ? load_stream<true>(ccode + pos, pol_stream) : 0u;
+        }
+        Acc xv[U][NB];
+#pragma unroll
+        for (int u = 0; u < U; ++u) load_xrow<NB>(xt + (u64)idx[u] * NB, pol_x, xv[u]);
+        // NOTE (SASS, not yet measured): ptxas software-pipelines this loop two gathers deep at 40
+        // registers (6 blocks/SM) instead of issuing all U first; a warp fence is hoisted above the
+        // gathers and a block fence costs a MEMBAR.SC -- to be tuned on hardware.
+        // branch-free: a dead slot multiplies x[self] by zero, so that the gathers above cannot be
+        // sunk into per-element conditionals (which serialises them)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          bool const live = j0 + u < len;
+          double const* t = table + 3 * code[u];
+          if constexpr (CPLX) {
+            double2 w = make_double2(live ? t[0] : 0.0, live ? t[1] : 0.0);
+            if constexpr (SYM) {
+              double const scale = t[2] * inv_nr;
+              w.x *= scale;
+              w.y *= scale;
+            }
+#pragma unroll
+            for (int c = 0; c < NB; ++c) acc_fma(acc[c], w, xv[u][c]);
+          } else {
+            double w = live ? t[0] : 0.0;
+            if constexpr (SYM) w = w * (t[2] * inv_nr);
+#pragma unroll
+            for (int c = 0; c < NB; ++c) acc_fma(acc[c], w, xv[u][c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c < (int)p.ncols) TR::store(y + (u64)c * p.ys + i, acc[c]);
+  }
+}
+
 // SPED_CACHED_VARIANT (tuning knob, default = the measured best): bit 0 cache-policy loads,
 // bit 1 eight (instead of four) elements in flight per thread.  Measured on B200 (6x6, f64):
 // 0: 2.10 ms, 1: 1.90 ms, 2: 1.83 ms, 3: 1.66 ms; sixteen in flight (86 registers): 2.00 ms.
@@ -408,18 +553,33 @@ void launch_cached_nb(CachedParams const& p, cudaStream_t s) {
   else launch_cached_variant<T, NB, std::uint8_t, false>(p, s);
 }
 
+template <class T, int NB>
+void launch_block(CachedParams const& p, T const* x, u64 xs, u64 n_entries, T* scratch, cudaStream_t s) {
+  interleave_kernel<T, NB><<<persistent_grid(n_entries, kThreads, 8), kThreads, 0, s>>>(x, xs, p.ncols, n_entries, scratch);
+  KERNEL_LAUNCHED();
+  CachedParams q = p;
+  q.x = scratch;
+  constexpr int U = NB == 2 ? 8 : 4;  // 32 accumulator-typed values in flight either way
+  bool const wide = p.cache.code_wide != 0, sym = p.sym != 0;
+  if (wide && sym) launch_cached_kernel<cached_block_kernel<T, NB, std::uint16_t, true, U>>(q, s);
+  else if (wide) launch_cached_kernel<cached_block_kernel<T, NB, std::uint16_t, false, U>>(q, s);
+  else if (sym) launch_cached_kernel<cached_block_kernel<T, NB, std::uint8_t, true, U>>(q, s);
+  else launch_cached_kernel<cached_block_kernel<T, NB, std::uint8_t, false, U>>(q, s);
+}
+
+// `scratch` holds the interleaved copy of up to four columns (n_entries * 4 values)
 template <class T>
-void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
+void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, u64 n_entries, void* scratch, cudaStream_t s) {
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
   for (u64 c0 = 0; c0 < block;) {
     u64 left = block - c0;
     p.x = x + c0 * xs;
     p.y = y + c0 * ys;
-    bool wide = left > 1;
-    p.ncols = (u32)std::min<u64>(left, wide ? 4 : 1);
-    if (wide) launch_cached_nb<T, 4>(p, s);
-    else launch_cached_nb<T, 1>(p, s);
+    p.ncols = (u32)std::min<u64>(left, 4);
+    if (p.ncols == 1) launch_cached_nb<T, 1>(p, s);
+    else if (p.ncols == 2) launch_block<T, 2>(p, x + c0 * xs, xs, n_entries, static_cast<T*>(scratch), s);
+    else launch_block<T, 4>(p, x + c0 * xs, xs, n_entries, static_cast<T*>(scratch), s);
     KERNEL_LAUNCHED();
     c0 += p.ncols;
   }
@@ -698,11 +858,19 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   p.row_hi = std::min<u64>(row_hi, dist.n_local);
   if (p.row_lo >= p.row_hi) return;
   if (p.row_lo & 31) fail(SPED_INTERNAL_ERROR, "row ranges of the cached matvec start at a multiple of 32");
+  u64 const n_entries = dist.chunk * dist.world;  // entries of one replicated column
+  void* scratch = nullptr;
+  if (block > 1) {
+    if (phase != kPhaseAll) fail(SPED_INTERNAL_ERROR, "block applications handle all source classes in one pass");
+    size_t const need_bytes = n_entries * 4 * dtype_size(dtype);
+    if (block_x.count < need_bytes) block_x.alloc(need_bytes);
+    scratch = block_x.ptr;
+  }
   switch (dtype) {
-    case SPED_F32: launch_cached<float>(p, block, xs, ys, s); break;
-    case SPED_F64: launch_cached<double>(p, block, xs, ys, s); break;
-    case SPED_C64: launch_cached<float2>(p, block, xs, ys, s); break;
-    case SPED_C128: launch_cached<double2>(p, block, xs, ys, s); break;
+    case SPED_F32: launch_cached<float>(p, block, xs, ys, n_entries, scratch, s); break;
+    case SPED_F64: launch_cached<double>(p, block, xs, ys, n_entries, scratch, s); break;
+    case SPED_C64: launch_cached<float2>(p, block, xs, ys, n_entries, scratch, s); break;
+    case SPED_C128: launch_cached<double2>(p, block, xs, ys, n_entries, scratch, s); break;
     default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
   }
 }
