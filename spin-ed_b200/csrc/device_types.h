@@ -120,7 +120,8 @@ struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
   u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
-  dev_u16 const* len;    // [n_classes][local rows] stored elements of the row per class
+  dev_u16 const* len;    // [2 * n_classes][local rows]: per source class the elements that carry the
+                         // default coefficient (no code is read for them), then the coded ones
   u32 const* slice_start;  // [n_slices][2] first slot of class 1 and of class 2; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
@@ -128,6 +129,12 @@ struct CacheView {
   u32 n_codes;           // entries of `table`
   u32 n_classes;         // 1 (single rank), 2 or 3
   u32 near;              // class 1 = owners rank+1 .. rank+near (mod world)
+  u32 default_code;      // the coefficient almost every element carries (first matrix value, chi = 1,
+                         // trivial stabiliser).  Inside its class region [start_c, start_c+1) a row keeps
+                         // these elements from the front, s = start_c + j, and the others -- with
+                         // their code -- from the back, s = start_c+1 - 1 - j ("two-ended"), so one
+                         // traversal fills both without knowing their numbers in advance.
+  u32 pad_;
 };
 
 // class of the entry at position `pos` of the replicated vector, seen from rank d.rank
@@ -145,7 +152,9 @@ struct FillParams {
   u64 const* slice_off;
   u32* idx;
   void* code;              // u8 or u16 per slot, see code_wide
-  dev_u16* len;            // [n_classes][local rows]
+  dev_u16* len;            // [2 * n_classes][local rows] (see CacheView)
+  u32 default_code;
+  u32 pad1_;
   u32 const* slice_start;  // several classes, fill pass: [n_slices][2] (see CacheView); null otherwise
   int count_only;          // several classes, first pass: only `len` is written
   u32 n_classes;

@@ -235,7 +235,9 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       start[2] = p.n_classes > 2 ? __ldg(p.slice_start + 2 * slice + 1) : width;
       start[3] = width;
     }
-    u32 cnt[kMaxClasses] = {0u, 0u, 0u};
+    // per class: cd = elements with the default coefficient (stored from the front of the class
+    // region), cx = coded elements (stored from its back).  Constant indices only: registers.
+    u32 cd[kMaxClasses] = {0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -244,28 +246,45 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
       u32 const cls = dist_source_class(dist, pos, p.n_classes, p.near);
-      // (constant indices only: the counters stay in registers)
-      u32 const have = cls == 0 ? cnt[0] : cls == 1 ? cnt[1] : cnt[2];
-      if (cls == 0) ++cnt[0]; else if (cls == 1) ++cnt[1]; else ++cnt[2];
-      if (count_only) return;
-      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
-      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
-      if (lo + have >= hi) {
-        *p.overflow = 1;
-        return;
-      }
-      u64 const at = base + (u64)(lo + have) * 32;
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
       u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
+      bool const dflt = code == p.default_code;
+      u32 const nd = cls == 0 ? cd[0] : cls == 1 ? cd[1] : cd[2];
+      u32 const nx = cls == 0 ? cx[0] : cls == 1 ? cx[1] : cx[2];
+      if (dflt) { if (cls == 0) ++cd[0]; else if (cls == 1) ++cd[1]; else ++cd[2]; }
+      else { if (cls == 0) ++cx[0]; else if (cls == 1) ++cx[1]; else ++cx[2]; }
+      if (count_only) return;
+      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
+      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
+      if (lo + nd + nx >= hi) {  // the two ends would meet
+        *p.overflow = 1;
+        return;
+      }
+      u64 const at = base + (u64)(dflt ? lo + nd : hi - 1u - nx) * 32;
       p.idx[at] = (u32)pos;
-      if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
-      else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
+      if (!dflt) {
+        if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
+        else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
+      }
     });
-    p.len[i] = (dev_u16)cnt[0];
-    if (p.n_classes > 1) p.len[n_local + i] = (dev_u16)cnt[1];
-    if (p.n_classes > 2) p.len[2 * n_local + i] = (dev_u16)cnt[2];
+    if (count_only) {  // class sizes only: the width pass needs cd + cx per class
+      p.len[i] = (dev_u16)(cd[0] + cx[0]);
+      if (p.n_classes > 1) p.len[2 * n_local + i] = (dev_u16)(cd[1] + cx[1]);
+      if (p.n_classes > 2) p.len[4 * n_local + i] = (dev_u16)(cd[2] + cx[2]);
+    } else {
+      p.len[i] = (dev_u16)cd[0];
+      p.len[n_local + i] = (dev_u16)cx[0];
+      if (p.n_classes > 1) {
+        p.len[2 * n_local + i] = (dev_u16)cd[1];
+        p.len[3 * n_local + i] = (dev_u16)cx[1];
+      }
+      if (p.n_classes > 2) {
+        p.len[4 * n_local + i] = (dev_u16)cd[2];
+        p.len[5 * n_local + i] = (dev_u16)cx[2];
+      }
+    }
   }
 }
 

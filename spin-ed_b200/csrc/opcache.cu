@@ -5,13 +5,15 @@
 //
 // The reference recomputes every matrix element in every ls_operator_matmat call
 // (/root/reference/src/SpinED/Internal.hs:411-429 is called once per PRIMME block per iteration).
-// Results are bit-identical to the matrix-free kernel: same elements, same order, and the
-// coefficient is rebuilt from the same factors,  w = v * (norm_s * (1 / norm_r)).
+// Results agree with the matrix-free kernel to rounding: same elements and the same coefficient
+// factors, w = v * (norm_s * (1 / norm_r)), but the elements that carry the default coefficient
+// (first matrix value, chi = 1, trivial stabiliser: almost all of them) are stored first, without a
+// code, and their x entries are summed before the one multiplication.
 //
-// Layout (sliced ELL): rows in slices of 32 = one warp; element j of lane l of slice s is at
-// slice_off[s] + 32 j + l.  Column indices are u32 (N < 2^32), coefficient codes u8 (u16 when there
-// are more than 256 distinct (value, phase, stabiliser) triples) into a table of (Re v, Im v,
-// norm_s), v = M[a][b] * chi(g').  5 or 6 bytes per element.
+// Layout (sliced ELL): rows in slices of 32 = one warp; slot j of lane l of slice s is at
+// slice_off[s] + 32 j + l.  Positions are u32 (N < 2^32); coded elements carry a u8 code (u16 when
+// there are more than 256 distinct (value, phase, stabiliser) triples) into a table of
+// (Re v, Im v, norm_s), v = M[a][b] * chi(g').  4 bytes per default element, 5 or 6 per coded one.
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t con
     u32 w[kMaxClasses] = {0u, 0u, 0u};
 #pragma unroll
     for (u32 c = 0; c < (u32)kMaxClasses; ++c) {
-      u32 v = (c < n_classes && i < n_local) ? len[(u64)c * n_local + i] : 0u;
+      u32 v = (c < n_classes && i < n_local) ? len[(u64)(2 * c) * n_local + i] : 0u;  // count pass: class totals
       w[c] = __reduce_max_sync(0xffffffffu, v);
     }
     if ((i & 31) == 0) {
@@ -237,7 +239,7 @@ template <bool HINT> __device__ __forceinline__ double2 load_x(double2 const* a,
 // and code loads are issued first, then the U gathers, then the U multiply-adds in order, so every
 // thread keeps U independent gathers in flight.
 template <class T, int NB, class Code, bool SYM, bool HINT, int U>
-__global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p) {
+__global__ void __launch_bounds__(kThreads, Traits<T>::cplx ? 1 : (U == 8 ? 5 : 6)) cached_matvec_kernel(CachedParams p) {
   typedef Traits<T> TR;
   typedef typename TR::Acc Acc;
   constexpr bool CPLX = TR::cplx;
@@ -288,68 +290,89 @@ __global__ void __launch_bounds__(kThreads) cached_matvec_kernel(CachedParams p)
       }
     }
     u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
-    // the stored elements of this lane, class by class, in stored order (one copy of the loop body:
-    // a second inlined copy costs 15 registers and with them a resident block per SM)
+    // the stored elements of this lane: per source class first the elements that carry the default
+    // coefficient (front of the class region, no code: their x entries are summed and multiplied
+    // once), then the coded ones (back of the region, downwards).  One copy of the loop body: a
+    // second inlined copy costs 15 registers and with them a resident block per SM.
+    u32 const width = (u32)((__ldg(p.cache.slice_off + (i >> 5) + 1) - __ldg(p.cache.slice_off + (i >> 5))) >> 5);
 #pragma unroll 1
-    for (u32 seg = seg_lo; seg < seg_hi; ++seg) {
-      u32 const first = seg == 0 ? 0u : __ldg(p.cache.slice_start + 2 * (i >> 5) + (seg - 1));
+    for (u32 seg = 2 * seg_lo; seg < 2 * seg_hi; ++seg) {
+      u32 const cls = seg >> 1;
+      bool const coded = (seg & 1u) != 0;
       u32 const len = __ldg(p.cache.len + (u64)seg * n_rows + i);
-      u64 const base = slice_base + (u64)first * 32;
-      for (u32 j0 = 0; j0 < len; j0 += U) {
-        u32 idx[U], code[U];
+      u32 const lo = cls == 0 ? 0u : __ldg(p.cache.slice_start + 2 * (i >> 5) + (cls - 1));
+      u32 const hi = cls + 1 == p.cache.n_classes ? width : __ldg(p.cache.slice_start + 2 * (i >> 5) + cls);
+      // element j sits at slot lo + j (default coefficient) or hi - 1 - j (coded)
+      u32 const slot0 = coded ? hi - 1u : lo;
+      int const sstep = coded ? -1 : 1;
+      if constexpr (NB == 1) {
+        Acc part = acc_zero(Acc());  // this segment: sum of w x (coded) or of x (default coefficient)
+        for (u32 j0 = 0; j0 < len; j0 += U) {
+          // `coded` is laundered through a volatile move so that the compiler does not unswitch the
+          // loop on it: two specialised copies of the body cost 30 registers (80 instead of 48)
+          u32 coded_i;
+          asm volatile("mov.u32 %0, %1;" : "=r"(coded_i) : "r"(seg & 1u));
+          bool const coded = coded_i != 0;
+          u32 idx[U], code[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          bool const live = j0 + u < len;
-          u64 const pos = base + (u64)(j0 + u) * 32;
-          idx[u] = live ? load_stream<HINT>(cidx + pos, pol_stream) : (u32)(self0 + i);
-          code[u] = live ? load_stream<HINT>(ccode + pos, pol_stream) : 0u;
-        }
-        if constexpr (NB == 1) {
+          for (int u = 0; u < U; ++u) {
+            bool const live = j0 + u < len;
+            u64 const pos = slice_base + (u64)(slot0 + (u32)(sstep * (int)(j0 + u))) * 32;
+            idx[u] = live ? load_stream<HINT>(cidx + pos, pol_stream) : (u32)(self0 + i);
+            code[u] = (live && coded) ? load_stream<HINT>(ccode + pos, pol_stream) : 0u;
+          }
           Acc xv[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) xv[u] = load_x<HINT>(x + idx[u], pol_x);  // dead slots re-read x[self]: an L1 hit
+          // one accumulate path for both kinds: coded elements look their coefficient up, the
+          // others add x itself (the common coefficient is applied once, after the loop)
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             if (j0 + u < len) {
-              double const* t = table + 3 * code[u];
               if constexpr (CPLX) {
-                double2 w = make_double2(t[0], t[1]);
-                if constexpr (SYM) {
-                  double const scale = t[2] * inv_nr;
-                  w.x *= scale;
-                  w.y *= scale;
+                double2 w = make_double2(1.0, 0.0);
+                if (coded) {
+                  double const* t = table + 3 * code[u];
+                  w = make_double2(t[0], t[1]);
+                  if constexpr (SYM) {
+                    double const scale = t[2] * inv_nr;
+                    w.x *= scale;
+                    w.y *= scale;
+                  }
                 }
-                acc_fma(acc[0], w, xv[u]);
+                acc_fma(part, w, xv[u]);
               } else {
-                double w = t[0];
-                if constexpr (SYM) w = w * (t[2] * inv_nr);
-                acc_fma(acc[0], w, xv[u]);
+                double w = 1.0;
+                if (coded) {
+                  double const* t = table + 3 * code[u];
+                  w = t[0];
+                  if constexpr (SYM) w = w * (t[2] * inv_nr);
+                }
+                acc_fma(part, w, xv[u]);
               }
             }
           }
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (j0 + u < len) {
-              double const* t = table + 3 * code[u];
-              if constexpr (CPLX) {
-                double2 w = make_double2(t[0], t[1]);
-                if constexpr (SYM) {
-                  double const scale = t[2] * inv_nr;
-                  w.x *= scale;
-                  w.y *= scale;
-                }
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                  if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
-              } else {
-                double w = t[0];
-                if constexpr (SYM) w = w * (t[2] * inv_nr);
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                  if (c < (int)p.ncols) acc_fma(acc[c], w, load_x<HINT>(x + (u64)c * p.xs + idx[u], pol_x));
+        }
+        {  // acc += part (coded) or w_default * part
+          double const* t = table + 3 * p.cache.default_code;
+          if constexpr (CPLX) {
+            double2 w = make_double2(1.0, 0.0);
+            if (!coded) {
+              w = make_double2(t[0], t[1]);
+              if constexpr (SYM) {
+                double const scale = t[2] * inv_nr;
+                w.x *= scale;
+                w.y *= scale;
               }
             }
+            acc_fma(acc[0], w, part);
+          } else {
+            double w = 1.0;
+            if (!coded) {
+              w = t[0];
+              if constexpr (SYM) w = w * (t[2] * inv_nr);
+            }
+            acc_fma(acc[0], w, part);
           }
         }
       }
@@ -455,19 +478,24 @@ __global__ void __launch_bounds__(kThreads) cached_block_kernel(CachedParams p) 
       }
     }
     u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
+    u32 const width = (u32)((__ldg(p.cache.slice_off + (i >> 5) + 1) - __ldg(p.cache.slice_off + (i >> 5))) >> 5);
 #pragma unroll 1
-    for (u32 seg = 0; seg < p.cache.n_classes; ++seg) {
-      u32 const first = seg == 0 ? 0u : __ldg(p.cache.slice_start + 2 * (i >> 5) + (seg - 1));
+    for (u32 seg = 0; seg < 2 * p.cache.n_classes; ++seg) {  // (class, default-coefficient | coded), see CacheView
+      u32 const cls = seg >> 1;
+      bool const coded = (seg & 1u) != 0;
       u32 const len = __ldg(p.cache.len + (u64)seg * n_rows + i);
-      u64 const base = slice_base + (u64)first * 32;
+      u32 const lo = cls == 0 ? 0u : __ldg(p.cache.slice_start + 2 * (i >> 5) + (cls - 1));
+      u32 const hi = cls + 1 == p.cache.n_classes ? width : __ldg(p.cache.slice_start + 2 * (i >> 5) + cls);
+      long long const step = coded ? -32ll : 32ll;
+      u64 const base = slice_base + (u64)(coded ? hi - 1u : lo) * 32;
       for (u32 j0 = 0; j0 < len; j0 += U) {
         u32 idx[U], code[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           bool const live = j0 + u < len;
-          u64 const pos = base + (u64)(j0 + u) * 32;
+          u64 const pos = (u64)((long long)base + step * (long long)(j0 + u));
           idx[u] = live ? load_stream<true>(cidx + pos, pol_stream) : (u32)(self0 + i);
-          code[u] = live ? load_stream<true>(ccode + pos, pol_stream) : 0u;
+          code[u] = (live && coded) ? load_stream<true>(ccode + pos, pol_stream) : p.cache.default_code;
         }
         Acc xv[U][NB];
 #pragma unroll
@@ -730,7 +758,7 @@ bool Operator::cache_usable() {
   bool const two = c_classes > 1;
   MatvecParams mp = operator_params(*this);
   size_t tsm = terms_smem_bytes(mp.terms, false);
-  c_len.alloc(n_local * c_classes);
+  c_len.alloc(n_local * 2 * c_classes);
   DeviceBuffer<int> d_flag(1);
   CUDA_CHECK(cudaMemset(d_flag.ptr, 0, sizeof(int)));
   FillParams fp{};
@@ -739,6 +767,9 @@ bool Operator::cache_usable() {
   fp.len = c_len.ptr;
   fp.n_classes = c_classes;
   fp.near = c_near;
+  // the coefficient almost every element carries: first off-diagonal value, chi = 1, trivial stabiliser
+  c_default_code = ((0u * n_pid + (sym ? (u32)pid_map[0] : 0u)) * (u32)sid_stab.size()) + (sym ? (u32)sid_map[1] : 0u);
+  fp.default_code = c_default_code;
   fp.hid_map = d_hid.ptr;
   fp.sid_map = sym ? d_sid_map.ptr : nullptr;
   fp.pid_map = sym ? d_pid_map.ptr : nullptr;
@@ -793,7 +824,7 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * (4 + code_bytes) + n_local * 2 * c_classes + (c_slices + 1) * (two ? 16 : 8) + n_codes * 24;
+  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (two ? 16 : 8) + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
@@ -821,7 +852,7 @@ bool Operator::cache_usable() {
 void Operator::cached_count(unsigned long long* d_out) {
   u64 n_local = dist.n_local;
   if (!n_local) return;
-  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local * c_classes, d_out);
+  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local * 2 * c_classes, d_out);
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
 }
@@ -843,7 +874,7 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
   p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_slice_start.ptr, c_table.ptr, c_slices,
-                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near};
+                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, 0u};
   p.phase = phase;
   p.beside_transfer = beside_transfer ? 1 : 0;
   p.ctx = mp.ctx;

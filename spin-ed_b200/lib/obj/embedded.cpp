@@ -122,7 +122,8 @@ struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
   u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
-  dev_u16 const* len;    // [n_classes][local rows] stored elements of the row per class
+  dev_u16 const* len;    // [2 * n_classes][local rows]: per source class the elements that carry the
+                         // default coefficient (no code is read for them), then the coded ones
   u32 const* slice_start;  // [n_slices][2] first slot of class 1 and of class 2; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
@@ -130,6 +131,12 @@ struct CacheView {
   u32 n_codes;           // entries of `table`
   u32 n_classes;         // 1 (single rank), 2 or 3
   u32 near;              // class 1 = owners rank+1 .. rank+near (mod world)
+  u32 default_code;      // the coefficient almost every element carries (first matrix value, chi = 1,
+                         // trivial stabiliser).  Inside its class region [start_c, start_c+1) a row keeps
+                         // these elements from the front, s = start_c + j, and the others -- with
+                         // their code -- from the back, s = start_c+1 - 1 - j ("two-ended"), so one
+                         // traversal fills both without knowing their numbers in advance.
+  u32 pad_;
 };
 
 // class of the entry at position `pos` of the replicated vector, seen from rank d.rank
@@ -147,7 +154,9 @@ struct FillParams {
   u64 const* slice_off;
   u32* idx;
   void* code;              // u8 or u16 per slot, see code_wide
-  dev_u16* len;            // [n_classes][local rows]
+  dev_u16* len;            // [2 * n_classes][local rows] (see CacheView)
+  u32 default_code;
+  u32 pad1_;
   u32 const* slice_start;  // several classes, fill pass: [n_slices][2] (see CacheView); null otherwise
   int count_only;          // several classes, first pass: only `len` is written
   u32 n_classes;
@@ -402,7 +411,9 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       start[2] = p.n_classes > 2 ? __ldg(p.slice_start + 2 * slice + 1) : width;
       start[3] = width;
     }
-    u32 cnt[kMaxClasses] = {0u, 0u, 0u};
+    // per class: cd = elements with the default coefficient (stored from the front of the class
+    // region), cx = coded elements (stored from its back).  Constant indices only: registers.
+    u32 cd[kMaxClasses] = {0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -411,28 +422,45 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
       u32 const cls = dist_source_class(dist, pos, p.n_classes, p.near);
-      // (constant indices only: the counters stay in registers)
-      u32 const have = cls == 0 ? cnt[0] : cls == 1 ? cnt[1] : cnt[2];
-      if (cls == 0) ++cnt[0]; else if (cls == 1) ++cnt[1]; else ++cnt[2];
-      if (count_only) return;
-      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
-      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
-      if (lo + have >= hi) {
-        *p.overflow = 1;
-        return;
-      }
-      u64 const at = base + (u64)(lo + have) * 32;
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
       u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
+      bool const dflt = code == p.default_code;
+      u32 const nd = cls == 0 ? cd[0] : cls == 1 ? cd[1] : cd[2];
+      u32 const nx = cls == 0 ? cx[0] : cls == 1 ? cx[1] : cx[2];
+      if (dflt) { if (cls == 0) ++cd[0]; else if (cls == 1) ++cd[1]; else ++cd[2]; }
+      else { if (cls == 0) ++cx[0]; else if (cls == 1) ++cx[1]; else ++cx[2]; }
+      if (count_only) return;
+      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
+      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
+      if (lo + nd + nx >= hi) {  // the two ends would meet
+        *p.overflow = 1;
+        return;
+      }
+      u64 const at = base + (u64)(dflt ? lo + nd : hi - 1u - nx) * 32;
       p.idx[at] = (u32)pos;
-      if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
-      else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
+      if (!dflt) {
+        if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
+        else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
+      }
     });
-    p.len[i] = (dev_u16)cnt[0];
-    if (p.n_classes > 1) p.len[n_local + i] = (dev_u16)cnt[1];
-    if (p.n_classes > 2) p.len[2 * n_local + i] = (dev_u16)cnt[2];
+    if (count_only) {  // class sizes only: the width pass needs cd + cx per class
+      p.len[i] = (dev_u16)(cd[0] + cx[0]);
+      if (p.n_classes > 1) p.len[2 * n_local + i] = (dev_u16)(cd[1] + cx[1]);
+      if (p.n_classes > 2) p.len[4 * n_local + i] = (dev_u16)(cd[2] + cx[2]);
+    } else {
+      p.len[i] = (dev_u16)cd[0];
+      p.len[n_local + i] = (dev_u16)cx[0];
+      if (p.n_classes > 1) {
+        p.len[2 * n_local + i] = (dev_u16)cd[1];
+        p.len[3 * n_local + i] = (dev_u16)cx[1];
+      }
+      if (p.n_classes > 2) {
+        p.len[4 * n_local + i] = (dev_u16)cd[2];
+        p.len[5 * n_local + i] = (dev_u16)cx[2];
+      }
+    }
   }
 }
 
