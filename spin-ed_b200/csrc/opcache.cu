@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(kThreads, Traits<T>::cplx ? 1 : (U == 8 ? 5 : 
             }
           }
         }
-        {  // acc += part (coded) or w_default * part
-          double const* t = table + 3 * p.cache.default_code;
+        if (len) {  // acc += part (coded) or w_default * part
+          double const* t = table + 3 * p.cache.default_code;  // only dereferenced for a non-empty default segment
           if constexpr (CPLX) {
             double2 w = make_double2(1.0, 0.0);
             if (!coded) {
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kThreads) cached_block_kernel(CachedParams p) 
           bool const live = j0 + u < len;
           u64 const pos = (u64)((long long)base + step * (long long)(j0 + u));
           idx[u] = live ? load_stream<true>(cidx + pos, pol_stream) : (u32)(self0 + i);
-          code[u] = (live && coded) ? load_stream<true>(ccode + pos, pol_stream) : p.cache.default_code;
+          code[u] = live ? (coded ? load_stream<true>(ccode + pos, pol_stream) : p.cache.default_code) : 0u;
         }
         Acc xv[U][NB];
 #pragma unroll
@@ -769,6 +769,8 @@ bool Operator::cache_usable() {
   fp.near = c_near;
   // the coefficient almost every element carries: first off-diagonal value, chi = 1, trivial stabiliser
   c_default_code = ((0u * n_pid + (sym ? (u32)pid_map[0] : 0u)) * (u32)sid_stab.size()) + (sym ? (u32)sid_map[1] : 0u);
+  if (char const* e = std::getenv("SPED_DEFAULT_CLASS"))
+    if (e[0] == '0') c_default_code = ~0u;  // tuning / diagnosis: no element matches, everything is stored coded
   fp.default_code = c_default_code;
   fp.hid_map = d_hid.ptr;
   fp.sid_map = sym ? d_sid_map.ptr : nullptr;
