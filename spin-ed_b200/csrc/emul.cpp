@@ -1,0 +1,315 @@
+// emul.cpp -- single-threaded HOST emulation of the matvec kernels, for the test-suite only.
+//
+// Compiled by the host compiler (never by nvcc): the CUDA built-ins the device code uses are
+// shimmed below (one "thread", one "block"), and the very same sources -- matvec_kernel.cuh
+// (matrix-free rows, cache fill) and cached_kernel.cuh (streaming kernel) -- run on small problems
+// so that slot arithmetic, source classes and summation logic can be checked against the oracle
+// without a GPU (tests/test_emulation.py).  The orchestration around the kernels (code maps,
+// slice widths, offsets) mirrors Operator::cache_usable with std::vector buffers.  This is a
+// verification hook (include/sped_selftest.h), not a compute path: nothing in the product calls it.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "internal.h"
+
+// ---- shims for the device built-ins (one thread, one block) ----
+#if !defined(__launch_bounds__)
+#define __launch_bounds__(...)
+#endif
+#define SPED_KERNEL_LINKAGE static
+namespace {
+struct Dim1 { unsigned x, y, z; };
+}
+static const Dim1 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
+template <class T> static inline T __ldg(T const* p) { return *p; }
+static inline void __syncthreads() {}
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+
+#include "canon.cuh"          // ProgramCanon, TrivialCanon (+ matvec_kernel.cuh)
+#include "cached_kernel.cuh"  // the streaming kernel
+
+namespace sped {
+namespace {
+
+struct Problem {
+  Operator& op;
+  Basis& b;
+  RowDist dist;
+  std::vector<u64> bucket;
+  std::vector<double> norm_table, chi_table, diag_re, diag_im;
+  std::vector<DevBond> bonds;
+  std::vector<double> pool_re, pool_im;
+  std::vector<std::uint16_t> masks;
+  std::vector<FastStep<u32>> fast32;
+  std::vector<PermOp<u32>> ops32;
+  BasisIndex ix{};
+  TermsView terms{};
+  RowContext ctx{};
+  bool sym;
+
+  Problem(Operator& o, u64 n, u64 const* reps, std::uint16_t const* stab, int world, int rank) : op(o), b(*o.basis) {
+    sym = !b.trivial();
+    dist = make_row_dist(n, world, rank);
+    bucket = {0, n, n};  // one prefix bucket holding everything (representatives are < 2^63)
+    ix.reps = reps;
+    ix.stab = sym ? stab : nullptr;
+    ix.bucket = bucket.data();
+    ix.n_states = n;
+    ix.bucket_shift = 63;
+    ix.bucket_count = 2;
+    ix.bucket_wide = 1;
+    ix.direct = 0;
+    u64 const order = b.group_order();
+    norm_table.resize(order + 1);
+    for (u64 s = 0; s <= order; ++s) norm_table[s] = std::sqrt((double)s / (double)order);
+    i64 const D = b.group->denom;
+    chi_table.resize(2 * (size_t)D);
+    for (i64 k = 0; k < D; ++k) {
+      long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)D;
+      chi_table[2 * k] = (double)std::cos(ang);
+      chi_table[2 * k + 1] = (double)std::sin(ang);
+      if (2 * k == D) { chi_table[2 * k] = -1.0; chi_table[2 * k + 1] = 0.0; }
+      if (k == 0) { chi_table[0] = 1.0; chi_table[1] = 0.0; }
+    }
+    packed_terms_host(op.terms, bonds, pool_re, pool_im, masks);
+    terms.bonds = bonds.data();
+    terms.pool_re = pool_re.data();
+    terms.pool_im = pool_im.data();
+    terms.masks = masks.data();
+    terms.n_bonds = (u32)bonds.size();
+    terms.pool_size = (u32)pool_re.size();
+    terms.mask_size = (u32)masks.size();
+    ctx = RowContext{ix, norm_table.data(), chi_table.data(), dist};
+    // diagonal of the local rows (what diagonal_kernel computes)
+    diag_re.assign(std::max<u64>(dist.n_local, 1), 0.0);
+    diag_im.assign(std::max<u64>(dist.n_local, 1), 0.0);
+    for (u64 i = 0; i < dist.n_local; ++i) {
+      u64 const r = reps[dist_local_to_global(dist, i)];
+      double re = 0, im = 0;
+      for (auto const& bd : bonds) {
+        u32 a = 0;
+        for (u32 j = 0; j < bd.k; ++j) a |= (u32)((r >> ((bd.sites >> (8 * j)) & 0xffu)) & 1ull) << (bd.k - 1 - j);
+        u32 const dim = 1u << bd.k;
+        re += pool_re[bd.moff + a * dim + a];
+        im += pool_im[bd.moff + a * dim + a];
+      }
+      diag_re[i] = re;
+      diag_im[i] = im;
+    }
+    auto const& P = b.program;
+    for (auto const& f : P.fast) fast32.push_back(FastStep<u32>{(u32)f.mask, f.ctl});
+    for (auto const& q : P.ops) ops32.push_back(PermOp<u32>{(u32)q.mask, q.amount});
+  }
+  ProgramView<u64> view64() const {
+    auto const& P = b.program;
+    return ProgramView<u64>{P.fast.data(), P.steps.data(), P.ops.data(), P.phase.data(), (u32)P.steps.size(), (u32)P.ops.size(),
+                            P.n_spins, P.shift, P.inversion, P.denom};
+  }
+  ProgramView<u32> view32() const {
+    auto const& P = b.program;
+    return ProgramView<u32>{fast32.data(), P.steps.data(), ops32.data(), P.phase.data(), (u32)P.steps.size(), (u32)P.ops.size(),
+                            P.n_spins, 0, P.inversion, P.denom};
+  }
+  // calls f(canon) with the canonicalisation functor of this basis
+  template <class F>
+  void with_canon(F&& f) const {
+    if (!sym) f(TrivialCanon());
+    else if (b.use32()) f(ProgramCanon<u32>{view32()});
+    else f(ProgramCanon<u64>{view64()});
+  }
+};
+
+template <class T>
+void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* stats, u32 ncols, T* y_block) {
+  RowDist const& d = pr.dist;
+  u64 const n_local = d.n_local, padded = std::max<u64>(d.chunk * d.world, 1);
+  std::vector<T> xfull(padded, T{});
+  for (u64 g = 0; g < d.n; ++g) xfull[dist_global_to_pos(d, g)] = x_global[g];
+  bool const cplx_diag = !pr.op.real_diagonal;
+
+  // ---- matrix-free rows ----
+  MatvecParams mp{};
+  mp.ctx = pr.ctx;
+  mp.terms = pr.terms;
+  mp.diag_re = pr.diag_re.data();
+  mp.diag_im = cplx_diag ? pr.diag_im.data() : nullptr;
+  mp.x = xfull.data();
+  mp.y = y_free;
+  mp.xs = padded;
+  mp.ys = std::max<u64>(n_local, 1);
+  mp.ncols = 1;
+  pr.with_canon([&](auto const& canon) { matvec_rows<T, 1>(mp, pr.terms, canon); });
+
+  // ---- operator cache: maps, table, widths, offsets, fill (mirrors Operator::cache_usable) ----
+  CodeMaps cm;
+  if (char const* why = build_code_maps(pr.op, cm)) fail(LS_INVALID_ARGUMENT, std::string("no operator cache: ") + why);
+  u32 const n_sid = (u32)cm.sid_stab.size();
+  std::vector<double> table(3 * cm.n_codes);
+  for (u64 c = 0; c < cm.n_codes; ++c) {  // table_kernel
+    u32 sid = (u32)(c % n_sid), pid = (u32)((c / n_sid) % cm.n_pid), hid = (u32)(c / ((u64)n_sid * cm.n_pid));
+    u32 ph = pr.sym ? cm.pid_phase[pid] : 0u;
+    double vx = cm.values_re[hid], vy = cm.values_im[hid];
+    if (pr.sym) {
+      if (!pr.op.is_real()) {
+        double cx = pr.chi_table[2 * ph], cy = pr.chi_table[2 * ph + 1];
+        double nx = vx * cx - vy * cy, ny = vx * cy + vy * cx;
+        vx = nx;
+        vy = ny;
+      } else {
+        vx = ph == 0 ? vx : -vx;
+        vy = 0.0;
+      }
+    }
+    table[3 * c] = vx;
+    table[3 * c + 1] = vy;
+    table[3 * c + 2] = pr.sym ? pr.norm_table[cm.sid_stab[sid]] : 1.0;
+  }
+  u32 const n_classes = d.world == 1 ? 1u : 1u + (u32)exchange_rounds(d.world);
+  u32 const near = n_classes == 3 ? d.world / 2 : d.world - 1;
+  bool const wide = cm.n_codes > 256;
+  u64 const n_slices = (n_local + 31) / 32;
+  std::vector<std::uint16_t> len(std::max<u64>(n_local, 1) * 2 * n_classes, 0);
+  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_start(std::max<u64>(n_slices, 1) * 2, 0);
+  int overflow = 0;
+  FillParams fp{};
+  fp.ctx = pr.ctx;
+  fp.terms = pr.terms;
+  fp.len = len.data();
+  fp.n_classes = n_classes;
+  fp.near = near;
+  fp.default_code = cm.default_code;
+  fp.hid_map = cm.hid_map.data();
+  fp.sid_map = pr.sym ? cm.sid_map.data() : nullptr;
+  fp.pid_map = pr.sym ? cm.pid_map.data() : nullptr;
+  fp.denom = cm.n_pid;
+  fp.n_sid = n_sid;
+  fp.code_wide = wide ? 1 : 0;
+  fp.overflow = &overflow;
+  if (n_classes > 1) {
+    fp.count_only = 1;
+    pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
+    for (u64 s = 0; s < n_slices; ++s) {  // class_width_kernel
+      u32 w[kMaxClasses] = {0, 0, 0};
+      for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i)
+        for (u32 c = 0; c < n_classes; ++c) w[c] = std::max<u32>(w[c], len[(u64)(2 * c) * n_local + i]);
+      widths[s] = w[0] + w[1] + w[2];
+      slice_start[2 * s] = w[0];
+      slice_start[2 * s + 1] = w[0] + w[1];
+    }
+    fp.count_only = 0;
+    fp.slice_start = slice_start.data();
+  } else {
+    for (u64 s = 0; s < n_slices; ++s) {  // slice_width_kernel: cheap upper bound
+      u32 mx = 0;
+      for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i) {
+        u64 const r = pr.ix.reps[dist_local_to_global(d, i)];
+        u32 ub = 0;
+        for (auto const& bd : pr.bonds) {
+          u32 a = 0;
+          for (u32 j = 0; j < bd.k; ++j) a |= (u32)((r >> ((bd.sites >> (8 * j)) & 0xffu)) & 1ull) << (bd.k - 1 - j);
+          ub += (u32)__builtin_popcount((unsigned)pr.masks[bd.zoff + a]);
+        }
+        mx = std::max(mx, ub);
+      }
+      widths[s] = mx;
+    }
+  }
+  std::vector<u64> slice_off(n_slices + 1, 0);
+  for (u64 s = 0; s < n_slices; ++s) slice_off[s + 1] = slice_off[s] + 32ull * widths[s];
+  u64 const slots = slice_off[n_slices];
+  std::vector<u32> idx(std::max<u64>(slots, 1), 0xdeadbeefu);
+  std::vector<unsigned char> code(std::max<u64>(slots, 1) * (wide ? 2 : 1), 0xee);
+  fp.slice_off = slice_off.data();
+  fp.idx = idx.data();
+  fp.code = code.data();
+  std::fill(len.begin(), len.end(), 0);
+  pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
+  if (overflow) fail(SPED_INTERNAL_ERROR, "emulated cache fill: a row exceeded its slot bound");
+  u64 elements = 0, dflt = 0;
+  for (u32 seg = 0; seg < 2 * n_classes; ++seg)
+    for (u64 i = 0; i < n_local; ++i) {
+      elements += len[(u64)seg * n_local + i];
+      if (!(seg & 1)) dflt += len[(u64)seg * n_local + i];
+    }
+  stats[0] = slots;
+  stats[1] = elements;
+  stats[2] = dflt;
+  stats[3] = n_classes;
+
+  // ---- streaming kernel: all classes in one pass, then class by class ----
+  CachedParams cp{};
+  cp.cache = CacheView{slice_off.data(), idx.data(), code.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,
+                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, 0u};
+  cp.ctx = pr.ctx;
+  cp.diag_re = pr.diag_re.data();
+  cp.diag_im = cplx_diag ? pr.diag_im.data() : nullptr;
+  cp.x = xfull.data();
+  cp.xs = padded;
+  cp.ys = std::max<u64>(n_local, 1);
+  cp.ncols = 1;
+  cp.sym = pr.sym ? 1 : 0;
+  cp.row_lo = 0;
+  cp.row_hi = n_local;
+  auto launch = [&](T* y, int phase) {
+    cp.y = y;
+    cp.phase = phase;
+    if (wide && pr.sym) cached_matvec_kernel<T, 1, std::uint16_t, true, false, 8>(cp);
+    else if (wide) cached_matvec_kernel<T, 1, std::uint16_t, false, false, 8>(cp);
+    else if (pr.sym) cached_matvec_kernel<T, 1, std::uint8_t, true, false, 8>(cp);
+    else cached_matvec_kernel<T, 1, std::uint8_t, false, false, 8>(cp);
+  };
+  if (n_local) {
+    launch(y_all, 0);
+    for (u32 c = 0; c < n_classes; ++c) launch(y_phased, 1 + (int)c);
+  }
+  // ---- block kernel: columns c > 0 are x shifted cyclically by c rows (in global order) ----
+  if (ncols > 1 && n_local) {
+    std::vector<T> xcols(padded * ncols, T{});
+    for (u32 c = 0; c < ncols; ++c)
+      for (u64 g = 0; g < d.n; ++g) xcols[(u64)c * padded + dist_global_to_pos(d, g)] = x_global[(g + c) % d.n];
+    u32 const nb = ncols == 2 ? 2u : 4u;
+    std::vector<T> xt(padded * nb, T{});
+    if (nb == 2) interleave_kernel<T, 2>(xcols.data(), padded, ncols, padded, xt.data());
+    else interleave_kernel<T, 4>(xcols.data(), padded, ncols, padded, xt.data());
+    cp.x = xt.data();
+    cp.y = y_block;
+    cp.ncols = ncols;
+    cp.phase = 0;
+    auto go = [&](auto nbtag) {
+      constexpr int NB = decltype(nbtag)::value;
+      constexpr int U = NB == 2 ? 8 : 4;
+      if (wide && pr.sym) cached_block_kernel<T, NB, std::uint16_t, true, U>(cp);
+      else if (wide) cached_block_kernel<T, NB, std::uint16_t, false, U>(cp);
+      else if (pr.sym) cached_block_kernel<T, NB, std::uint8_t, true, U>(cp);
+      else cached_block_kernel<T, NB, std::uint8_t, false, U>(cp);
+    };
+    if (nb == 2) go(std::integral_constant<int, 2>());
+    else go(std::integral_constant<int, 4>());
+  }
+}
+
+}  // namespace
+}  // namespace sped
+
+using namespace sped;
+
+extern "C" int sped_selftest_emulate_matvec(void const* op_handle, uint64_t n, uint64_t const* reps, uint16_t const* stab,
+                                            int world, int rank, int dtype, void const* x_global, void* y_free, void* y_all,
+                                            void* y_phased, uint64_t* stats, unsigned ncols, void* y_block) {
+  return guard([&] {
+    auto& op = *static_cast<std::shared_ptr<Operator>*>(const_cast<void*>(op_handle));
+    if (dtype != SPED_F64 && dtype != SPED_C128) fail(LS_INVALID_DATATYPE, "the emulation handles f64 and c128");
+    if (dtype == SPED_F64 && !op->is_real()) fail(LS_OPERATOR_IS_COMPLEX, "operator is complex but a real datatype was requested");
+    Problem pr(*op, n, reps, stab, world, rank);
+    if (dtype == SPED_F64)
+      run<double>(pr, static_cast<double const*>(x_global), static_cast<double*>(y_free), static_cast<double*>(y_all),
+                  static_cast<double*>(y_phased), stats, ncols, static_cast<double*>(y_block));
+    else
+      run<double2>(pr, static_cast<double2 const*>(x_global), static_cast<double2*>(y_free), static_cast<double2*>(y_all),
+                   static_cast<double2*>(y_phased), stats, ncols, static_cast<double2*>(y_block));
+  });
+}

@@ -257,6 +257,18 @@ struct Operator {
 
 int exchange_rounds(unsigned world);  // opcache.cu
 
+// Code maps of the operator cache (opcache.cu, build_code_maps)
+struct CodeMaps {
+  std::vector<double> values_re, values_im;                            // distinct off-diagonal matrix values
+  std::vector<std::uint16_t> hid_map, sid_map, sid_stab, pid_map, pid_phase;
+  u32 n_pid = 1, default_code = 0;
+  u64 n_codes = 0;
+};
+char const* build_code_maps(Operator const& op, CodeMaps& out);
+// host copy of the packed terms (operator.cu): bonds in the order the kernels visit them
+void packed_terms_host(std::vector<Interaction> const& terms, std::vector<DevBond>& bonds, std::vector<double>& pool_re,
+                       std::vector<double>& pool_im, std::vector<std::uint16_t>& masks);
+
 std::shared_ptr<Interaction> make_interaction(int k, void const* matrix, unsigned count, std::uint16_t const* sites);
 std::shared_ptr<Operator> make_operator(std::shared_ptr<Basis> b, std::vector<Interaction const*> const& terms);
 

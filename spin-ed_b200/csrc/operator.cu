@@ -389,6 +389,15 @@ void Operator::matmat_device(int dtype, u64 block, void const* x, u64 xs, void* 
   }
 }
 
+void packed_terms_host(std::vector<Interaction> const& terms, std::vector<DevBond>& bonds, std::vector<double>& pool_re,
+                       std::vector<double>& pool_im, std::vector<std::uint16_t>& masks) {
+  PackedTerms pk = pack_terms(terms);
+  bonds = pk.bonds;
+  pool_re = pk.pool_re;
+  pool_im = pk.pool_im;
+  masks = pk.masks;
+}
+
 // One column, multi-rank: the all-gather of the Krylov vector runs on its own stream while the
 // streaming kernel already handles the elements whose source entries this rank owns; the remote
 // class follows once the gather has landed.  (Matrix-free mode: gather, then one kernel.)

@@ -123,6 +123,7 @@ SIGNATURES = {
     "sped_selftest_burnside": (_ci, [_vp, C.POINTER(_u64)]),
     "sped_selftest_jit_source": (_ci, [_vp, _vp, _u64, C.POINTER(_u64)]),
     "sped_selftest_jit_compile": (_ci, [_vp, _ci, _ci, C.POINTER(_u64)]),
+    "sped_selftest_emulate_matvec": (_ci, [_vp, _u64, _vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, C.c_uint, _vp]),
 }
 
 
