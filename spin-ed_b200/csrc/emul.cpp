@@ -26,6 +26,7 @@ struct Dim1 { unsigned x, y, z; };
 static const Dim1 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 template <class T> static inline T __ldg(T const* p) { return *p; }
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
@@ -168,12 +169,14 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
     table[3 * c + 1] = vy;
     table[3 * c + 2] = pr.sym ? pr.norm_table[cm.sid_stab[sid]] : 1.0;
   }
-  u32 const n_classes = d.world == 1 ? 1u : 1u + (u32)exchange_rounds(d.world);
-  u32 const near = n_classes == 3 ? d.world / 2 : d.world - 1;
+  u32 const rounds = (u32)exchange_rounds(d.world);
+  u32 const window = window_enabled() ? 1u : 0u;
+  u32 const n_classes = window + 1u + rounds;
+  u32 const near = rounds == 2 ? d.world / 2 : d.world - 1;
   bool const wide = cm.n_codes > 256;
   u64 const n_slices = (n_local + 31) / 32;
   std::vector<std::uint16_t> len(std::max<u64>(n_local, 1) * 2 * n_classes, 0);
-  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_start(std::max<u64>(n_slices, 1) * 2, 0);
+  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_start(std::max<u64>(n_slices, 1) * 3, 0);
   int overflow = 0;
   FillParams fp{};
   fp.ctx = pr.ctx;
@@ -181,6 +184,8 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   fp.len = len.data();
   fp.n_classes = n_classes;
   fp.near = near;
+  fp.window = window;
+  fp.rounds = rounds;
   fp.default_code = cm.default_code;
   fp.hid_map = cm.hid_map.data();
   fp.sid_map = pr.sym ? cm.sid_map.data() : nullptr;
@@ -189,16 +194,17 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   fp.n_sid = n_sid;
   fp.code_wide = wide ? 1 : 0;
   fp.overflow = &overflow;
-  if (n_classes > 1) {
+  if (rounds > 0) {  // several ranks: exact class sizes from a counting traversal
     fp.count_only = 1;
     pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
     for (u64 s = 0; s < n_slices; ++s) {  // class_width_kernel
-      u32 w[kMaxClasses] = {0, 0, 0};
+      u32 w[kMaxClasses] = {0, 0, 0, 0};
       for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i)
         for (u32 c = 0; c < n_classes; ++c) w[c] = std::max<u32>(w[c], len[(u64)(2 * c) * n_local + i]);
-      widths[s] = w[0] + w[1] + w[2];
-      slice_start[2 * s] = w[0];
-      slice_start[2 * s + 1] = w[0] + w[1];
+      widths[s] = w[0] + w[1] + w[2] + w[3];
+      slice_start[3 * s] = w[0];
+      slice_start[3 * s + 1] = w[0] + w[1];
+      slice_start[3 * s + 2] = w[0] + w[1] + w[2];
     }
     fp.count_only = 0;
     fp.slice_start = slice_start.data();
@@ -215,8 +221,13 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
         }
         mx = std::max(mx, ub);
       }
-      widths[s] = mx;
+      u32 const ws = window ? window_slots() : 0u;  // guessed width of the window region
+      widths[s] = mx + ws;
+      slice_start[3 * s] = ws;
+      slice_start[3 * s + 1] = mx + ws;
+      slice_start[3 * s + 2] = mx + ws;
     }
+    if (window) fp.slice_start = slice_start.data();
   }
   std::vector<u64> slice_off(n_slices + 1, 0);
   for (u64 s = 0; s < n_slices; ++s) slice_off[s + 1] = slice_off[s] + 32ull * widths[s];
@@ -235,15 +246,19 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
       elements += len[(u64)seg * n_local + i];
       if (!(seg & 1)) dflt += len[(u64)seg * n_local + i];
     }
+  u64 windowed = 0;
+  if (window)
+    for (u64 i = 0; i < n_local; ++i) windowed += len[i] + len[n_local + i];
   stats[0] = slots;
   stats[1] = elements;
   stats[2] = dflt;
   stats[3] = n_classes;
+  stats[4] = windowed;
 
   // ---- streaming kernel: all classes in one pass, then class by class ----
   CachedParams cp{};
   cp.cache = CacheView{slice_off.data(), idx.data(), code.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,
-                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, 0u};
+                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, window, rounds, 0u};
   cp.ctx = pr.ctx;
   cp.diag_re = pr.diag_re.data();
   cp.diag_im = cplx_diag ? pr.diag_im.data() : nullptr;
@@ -264,7 +279,7 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   };
   if (n_local) {
     launch(y_all, 0);
-    for (u32 c = 0; c < n_classes; ++c) launch(y_phased, 1 + (int)c);
+    for (u32 ph = 1; ph <= 1 + rounds; ++ph) launch(y_phased, (int)ph);  // local pass, then one pass per exchange round
   }
   // ---- block kernel: columns c > 0 are x shifted cyclically by c rows (in global order) ----
   if (ncols > 1 && n_local) {

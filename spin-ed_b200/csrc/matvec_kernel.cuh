@@ -55,24 +55,28 @@ template <> struct Traits<float> {
   typedef double Acc;
   static constexpr bool cplx = false;
   static __device__ __forceinline__ Acc load(float const* p) { return (double)__ldg(p); }
+  static __device__ __forceinline__ Acc to_acc(float v) { return (double)v; }
   static __device__ __forceinline__ void store(float* p, Acc v) { *p = (float)v; }
 };
 template <> struct Traits<double> {
   typedef double Acc;
   static constexpr bool cplx = false;
   static __device__ __forceinline__ Acc load(double const* p) { return __ldg(p); }
+  static __device__ __forceinline__ Acc to_acc(double v) { return v; }
   static __device__ __forceinline__ void store(double* p, Acc v) { *p = v; }
 };
 template <> struct Traits<float2> {
   typedef double2 Acc;
   static constexpr bool cplx = true;
   static __device__ __forceinline__ Acc load(float2 const* p) { float2 v = __ldg(p); return make_double2(v.x, v.y); }
+  static __device__ __forceinline__ Acc to_acc(float2 v) { return make_double2(v.x, v.y); }
   static __device__ __forceinline__ void store(float2* p, Acc v) { *p = make_float2((float)v.x, (float)v.y); }
 };
 template <> struct Traits<double2> {
   typedef double2 Acc;
   static constexpr bool cplx = true;
   static __device__ __forceinline__ Acc load(double2 const* p) { return __ldg(p); }
+  static __device__ __forceinline__ Acc to_acc(double2 v) { return v; }
   static __device__ __forceinline__ void store(double2* p, Acc v) { *p = v; }
 };
 
@@ -222,22 +226,21 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
   RowDist const dist = p.ctx.dist;
   u64 const n_local = dist.n_local;
   bool const count_only = p.count_only != 0;
+  u32 const nc = p.n_classes;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
     u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 base = 0;
-    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u};  // first slot of each class; start[n_classes] = width
+    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u, 0u};  // first slot of each class; start[c >= n_classes] = width
     if (!count_only) {
       base = __ldg(p.slice_off + slice) + (i & 31);
       u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
-      start[1] = p.n_classes > 1 ? __ldg(p.slice_start + 2 * slice) : width;
-      start[2] = p.n_classes > 2 ? __ldg(p.slice_start + 2 * slice + 1) : width;
-      start[3] = width;
+      for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(p.slice_start + 3 * slice + (c - 1)) : width;
     }
     // per class: cd = elements with the default coefficient (stored from the front of the class
-    // region), cx = coded elements (stored from its back).  Constant indices only: registers.
-    u32 cd[kMaxClasses] = {0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u};
+    // region), cx = coded elements (stored from its back)
+    u32 cd[kMaxClasses] = {0u, 0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -245,44 +248,37 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
-      u32 const cls = dist_source_class(dist, pos, p.n_classes, p.near);
+      u32 woff = 0;
+      u32 cls = dist_source_class(dist, pos, i, p.window, p.rounds, p.near, &woff);
+      // a full window region (its width is a guess when the classes are not counted first) sends
+      // the element to the plain local class, where every local source can live
+      if (!count_only && cls == 0 && p.window && cd[0] + cx[0] >= start[1] - start[0]) cls = 1;
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
       u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
       bool const dflt = code == p.default_code;
-      u32 const nd = cls == 0 ? cd[0] : cls == 1 ? cd[1] : cd[2];
-      u32 const nx = cls == 0 ? cx[0] : cls == 1 ? cx[1] : cx[2];
-      if (dflt) { if (cls == 0) ++cd[0]; else if (cls == 1) ++cd[1]; else ++cd[2]; }
-      else { if (cls == 0) ++cx[0]; else if (cls == 1) ++cx[1]; else ++cx[2]; }
+      u32 const nd = cd[cls], nx = cx[cls];
+      if (dflt) ++cd[cls]; else ++cx[cls];
       if (count_only) return;
-      u32 const lo = cls == 0 ? start[0] : cls == 1 ? start[1] : start[2];
-      u32 const hi = cls == 0 ? start[1] : cls == 1 ? start[2] : start[3];
+      u32 const lo = start[cls], hi = start[cls + 1];
       if (lo + nd + nx >= hi) {  // the two ends would meet
         *p.overflow = 1;
         return;
       }
       u64 const at = base + (u64)(dflt ? lo + nd : hi - 1u - nx) * 32;
-      p.idx[at] = (u32)pos;
+      p.idx[at] = (cls == 0 && p.window) ? woff : (u32)pos;
       if (!dflt) {
         if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
         else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
       }
     });
-    if (count_only) {  // class sizes only: the width pass needs cd + cx per class
-      p.len[i] = (dev_u16)(cd[0] + cx[0]);
-      if (p.n_classes > 1) p.len[2 * n_local + i] = (dev_u16)(cd[1] + cx[1]);
-      if (p.n_classes > 2) p.len[4 * n_local + i] = (dev_u16)(cd[2] + cx[2]);
-    } else {
-      p.len[i] = (dev_u16)cd[0];
-      p.len[n_local + i] = (dev_u16)cx[0];
-      if (p.n_classes > 1) {
-        p.len[2 * n_local + i] = (dev_u16)cd[1];
-        p.len[3 * n_local + i] = (dev_u16)cx[1];
-      }
-      if (p.n_classes > 2) {
-        p.len[4 * n_local + i] = (dev_u16)cd[2];
-        p.len[5 * n_local + i] = (dev_u16)cx[2];
+    for (u32 c = 0; c < nc; ++c) {
+      if (count_only) {  // class sizes only: the width pass needs cd + cx per class
+        p.len[(u64)(2 * c) * n_local + i] = (dev_u16)(cd[c] + cx[c]);
+      } else {
+        p.len[(u64)(2 * c) * n_local + i] = (dev_u16)cd[c];
+        p.len[(u64)(2 * c + 1) * n_local + i] = (dev_u16)cx[c];
       }
     }
   }

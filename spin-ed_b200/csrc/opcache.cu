@@ -31,7 +31,8 @@ namespace {
 
 // Upper bound of the row lengths (transitions with a non-zero matrix element, whether or not the
 // target survives the projection) and its maximum over each slice.
-__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths) {
+__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths, u32 window_slots,
+                                                               u32* slice_start) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(terms_g, smem);
   u64 const n_local = ctx.dist.n_local;
@@ -49,26 +50,36 @@ __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, T
       }
     }
     u32 mx = __reduce_max_sync(0xffffffffu, ub);
-    if ((i & 31) == 0) widths[i >> 5] = mx;
+    if ((i & 31) == 0) {
+      // window class in front (its width is a guess: what does not fit goes to the local class,
+      // which is wide enough for every element of the row), then the local class
+      widths[i >> 5] = mx + window_slots;
+      if (slice_start) {
+        slice_start[3 * (i >> 5)] = window_slots;
+        slice_start[3 * (i >> 5) + 1] = mx + window_slots;
+        slice_start[3 * (i >> 5) + 2] = mx + window_slots;
+      }
+    }
   }
 }
 
 // Several classes: per slice class c takes max_lanes len_c slots per lane; widths[s] is their sum
-// and slice_start[s] = (first slot of class 1, first slot of class 2).
+// and slice_start[s] = first slot of classes 1, 2, 3.
 __global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len, u64 n_local, u32 n_classes,
                                                                u32* widths, u32* slice_start) {
   u64 const n_padded = (n_local + 31) & ~(u64)31;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
-    u32 w[kMaxClasses] = {0u, 0u, 0u};
+    u32 w[kMaxClasses] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (u32 c = 0; c < (u32)kMaxClasses; ++c) {
       u32 v = (c < n_classes && i < n_local) ? len[(u64)(2 * c) * n_local + i] : 0u;  // count pass: class totals
       w[c] = __reduce_max_sync(0xffffffffu, v);
     }
     if ((i & 31) == 0) {
-      widths[i >> 5] = w[0] + w[1] + w[2];
-      slice_start[2 * (i >> 5)] = w[0];
-      slice_start[2 * (i >> 5) + 1] = w[0] + w[1];
+      widths[i >> 5] = w[0] + w[1] + w[2] + w[3];
+      slice_start[3 * (i >> 5)] = w[0];
+      slice_start[3 * (i >> 5) + 1] = w[0] + w[1];
+      slice_start[3 * (i >> 5) + 2] = w[0] + w[1] + w[2];
     }
   }
 }
@@ -324,6 +335,18 @@ char const* build_code_maps(Operator const& op, CodeMaps& out) {
   return nullptr;
 }
 
+// SPED_WINDOW=0 switches the window class off; SPED_WINDOW_SLOTS sets its width per lane when the
+// classes are not counted first (one rank): window-eligible elements beyond it go to the local class.
+bool window_enabled() {
+  char const* e = std::getenv("SPED_WINDOW");
+  return !(e && e[0] == '0');
+}
+unsigned window_slots() {
+  char const* e = std::getenv("SPED_WINDOW_SLOTS");
+  int v = e && *e ? std::atoi(e) : 16;
+  return (unsigned)std::max(1, std::min(v, 64));
+}
+
 void Operator::drop_cache() {
   cache_ready = false;
   cache_rejected = false;
@@ -334,6 +357,8 @@ void Operator::drop_cache() {
   c_slice_start.release();
   c_classes = 1;
   c_near = 0;
+  c_window = 0;
+  c_rounds = 0;
   c_table.release();
   c_slices = c_slots = cache_bytes = 0;
 }
@@ -387,9 +412,11 @@ bool Operator::cache_usable() {
   u64 const code_bytes = c_code_wide ? 2 : 1;
   // source classes (see CacheView): local / peers of the first exchange round / of the second
   u32 const world = dist.world;
-  c_classes = world == 1 ? 1 : 1 + (u32)exchange_rounds(world);
-  c_near = c_classes == 3 ? world / 2 : world - 1;  // 8 ranks: 4 peers in the first round, 3 in the second
-  bool const two = c_classes > 1;
+  c_rounds = (u32)exchange_rounds(world);
+  c_window = window_enabled() ? 1u : 0u;
+  c_classes = c_window + 1 + c_rounds;
+  c_near = c_rounds == 2 ? world / 2 : world - 1;  // 8 ranks: 4 peers in the first round, 3 in the second
+  bool const two = c_rounds > 0;  // several ranks: exact class sizes from a counting traversal
   MatvecParams mp = operator_params(*this);
   size_t tsm = terms_smem_bytes(mp.terms, false);
   c_len.alloc(n_local * 2 * c_classes);
@@ -401,6 +428,8 @@ bool Operator::cache_usable() {
   fp.len = c_len.ptr;
   fp.n_classes = c_classes;
   fp.near = c_near;
+  fp.window = c_window;
+  fp.rounds = c_rounds;
   c_default_code = cm_.default_code;
   fp.default_code = c_default_code;
   fp.hid_map = d_hid.ptr;
@@ -442,14 +471,20 @@ bool Operator::cache_usable() {
   if (two) {
     fp.count_only = 1;
     launch_fill();
-    c_slice_start.alloc(c_slices * 2);
+    c_slice_start.alloc(c_slices * 3);
     class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, d_widths.ptr,
                                                                                  c_slice_start.ptr);
     fp.count_only = 0;
     fp.slice_start = c_slice_start.ptr;
   } else {
     if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
+    if (c_window) {
+      c_slice_start.alloc(c_slices * 3);
+      fp.slice_start = c_slice_start.ptr;
+    }
+    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr,
+                                                                                 c_window ? window_slots() : 0u,
+                                                                                 c_window ? c_slice_start.ptr : nullptr);
   }
   KERNEL_LAUNCHED();
   c_slice_off.alloc(c_slices + 1);
@@ -457,7 +492,7 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (two ? 16 : 8) + n_codes * 24;
+  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 20 : 8) + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
@@ -507,7 +542,7 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
   p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_slice_start.ptr, c_table.ptr, c_slices,
-                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, 0u};
+                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_window, c_rounds, 0u};
   p.phase = phase;
   p.beside_transfer = beside_transfer ? 1 : 0;
   p.ctx = mp.ctx;

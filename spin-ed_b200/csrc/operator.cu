@@ -421,7 +421,7 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
     return;
   }
   bool const rounds = exchange_rounds(dist.world) == 2;
-  bool const cached = n_local > 0 && cache_usable() && c_classes == (rounds ? 3u : 2u);
+  bool const cached = n_local > 0 && cache_usable() && c_rounds == (rounds ? 2u : 1u);
   // SPED_OVERLAP_TRACE=n: device times of the first n overlapped matvecs
   static int trace_left = [] {
     char const* e = std::getenv("SPED_OVERLAP_TRACE");
@@ -471,7 +471,7 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
   }
   CUDA_CHECK(cudaStreamWaitEvent(s, cm.ev_gathered, 0));
   mark(7, s);
-  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, (int)c_classes, false);
+  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 1 + (int)c_rounds, false);
   mark(8, s);
   if (trace) {
     CUDA_CHECK(cudaStreamSynchronize(s));
