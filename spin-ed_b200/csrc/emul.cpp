@@ -172,7 +172,7 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   u32 const rounds = (u32)exchange_rounds(d.world);
   u32 const window = window_enabled() ? 1u : 0u;
   u32 const n_classes = window + 1u + rounds;
-  u32 const near = rounds == 2 ? d.world / 2 : d.world - 1;
+  u32 const near = exchange_near(d.world);
   bool const wide = cm.n_codes > 256;
   u64 const n_slices = (n_local + 31) / 32;
   std::vector<std::uint16_t> len(std::max<u64>(n_local, 1) * 2 * n_classes, 0);

@@ -256,6 +256,7 @@ struct Operator {
 };
 
 int exchange_rounds(unsigned world);  // opcache.cu
+unsigned exchange_near(unsigned world);
 bool window_enabled();                // opcache.cu
 unsigned window_slots();
 

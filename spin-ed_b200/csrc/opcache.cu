@@ -347,6 +347,10 @@ unsigned window_slots() {
   return (unsigned)std::max(1, std::min(v, 64));
 }
 
+// Peers of the first exchange round: ranks r+1 .. r+near (a function of the world size and the
+// environment only, like exchange_rounds: every rank must agree on who talks in which round).
+unsigned exchange_near(unsigned world) { return exchange_rounds(world) == 2 ? world / 2 : world - 1; }
+
 void Operator::drop_cache() {
   cache_ready = false;
   cache_rejected = false;
@@ -415,7 +419,7 @@ bool Operator::cache_usable() {
   c_rounds = (u32)exchange_rounds(world);
   c_window = window_enabled() ? 1u : 0u;
   c_classes = c_window + 1 + c_rounds;
-  c_near = c_rounds == 2 ? world / 2 : world - 1;  // 8 ranks: 4 peers in the first round, 3 in the second
+  c_near = exchange_near(world);  // 8 ranks: 4 peers in the first round, 3 in the second
   bool const two = c_rounds > 0;  // several ranks: exact class sizes from a counting traversal
   MatvecParams mp = operator_params(*this);
   size_t tsm = terms_smem_bytes(mp.terms, false);

@@ -440,10 +440,13 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
   CUDA_CHECK(cudaStreamWaitEvent(g, cm.ev_ready, 0));
   mark(0, g);
   if (rounds) {
-    comm_exchange_round(xfull, dist.chunk * es, 1, (int)c_near, g);
+    // (near comes from the world size, not from this rank's cache: a rank without rows or without a
+    // cache has to send and receive in the same rounds as everybody else)
+    int const near = (int)exchange_near(dist.world);
+    comm_exchange_round(xfull, dist.chunk * es, 1, near, g);
     CUDA_CHECK(cudaEventRecord(cm.ev_round1, g));
     mark(1, g);
-    comm_exchange_round(xfull, dist.chunk * es, (int)c_near + 1, (int)dist.world - 1, g);
+    comm_exchange_round(xfull, dist.chunk * es, near + 1, (int)dist.world - 1, g);
   } else {
     comm_allgather_inplace(xfull, dist.chunk * es, g);
     mark(1, g);
