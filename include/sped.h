@@ -177,8 +177,8 @@ int sped_operator_count_elements(void const* op, uint64_t* rows, uint64_t* offdi
 int sped_operator_diagonal(void const* op, double* out_local_rows);
 /* Operator cache.  By default (mode -1, or the SPED_OPERATOR_CACHE environment variable) the first
  * application of an operator is matrix-free and stores the off-diagonal elements it finds in HBM
- * when they fit in half of the free device memory; later applications stream them (bit-identical
- * results).  mode 0: always matrix-free; mode 1: cache whenever it fits at all.  Changing the mode
+ * when they fit in half of the free device memory; later applications stream them (same elements,
+ * results equal to rounding).  mode 0: always matrix-free; mode 1: cache whenever it fits at all.  Changing the mode
  * drops an existing cache. */
 int sped_operator_set_cache(void const* op, int mode);
 int sped_operator_cache_info(void const* op, int* ready, uint64_t* bytes, double* build_seconds);

@@ -26,9 +26,9 @@ int sped_selftest_jit_compile(void const* basis, int dtype, int columns, uint64_
  * by the host compiler with the CUDA built-ins shimmed) on a small problem whose representatives
  * and stabiliser sizes the caller supplies (the test-suite takes them from the oracle): y = H x for
  * the rows rank `rank` of `world` owns, computed by the matrix-free row routine (y_free), by the
- * streaming kernel over both source classes at once (y_all) and class by class (y_phased).
- * dtype: 1 = f64, 3 = c128; x in global row order.  stats[4] = slots, stored elements, elements
- * with a local source, source classes.  With ncols = 2..4 the multi-column variant is run as well
+ * streaming kernel over all source classes at once (y_all) and class by class (y_phased).
+ * dtype: 1 = f64, 3 = c128; x in global row order.  stats[5] = slots, stored elements, elements
+ * with the default coefficient, source classes, elements of the window class.  With ncols = 2..4 the block kernel is run as well
  * on the columns x_c[g] = x[(g + c) mod n] (y_block: n_local x ncols, column-major).
  * Verification only: nothing in the product calls it. */
 int sped_selftest_emulate_matvec(void const* op, uint64_t n, uint64_t const* reps, uint16_t const* stab, int world, int rank,

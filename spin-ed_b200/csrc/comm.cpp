@@ -25,6 +25,8 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -50,6 +52,8 @@ NcclApi& api() {
   a.AllGather = reinterpret_cast<decltype(a.AllGather)>(load("ncclAllGather"));
   a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(load("ncclAllReduce"));
   a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(load("ncclBroadcast"));
+  a.Send = reinterpret_cast<decltype(a.Send)>(load("ncclSend"));
+  a.Recv = reinterpret_cast<decltype(a.Recv)>(load("ncclRecv"));
   a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(load("ncclGroupStart"));
   a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(load("ncclGroupEnd"));
   a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(load("ncclGetErrorString"));
@@ -91,6 +95,7 @@ void comm_init(int world, int rank, void const* id128) {
   CUDA_CHECK(cudaStreamCreateWithPriority(&g_comm.gather_stream, cudaStreamNonBlocking, prio_hi));
   CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_ready, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_gathered, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_round1, cudaEventDisableTiming));
 }
 
 void comm_finalize() {
@@ -108,7 +113,8 @@ void comm_finalize() {
   }
   if (g_comm.ev_ready) cudaEventDestroy(g_comm.ev_ready);
   if (g_comm.ev_gathered) cudaEventDestroy(g_comm.ev_gathered);
-  g_comm.ev_ready = g_comm.ev_gathered = nullptr;
+  if (g_comm.ev_round1) cudaEventDestroy(g_comm.ev_round1);
+  g_comm.ev_ready = g_comm.ev_gathered = g_comm.ev_round1 = nullptr;
   g_comm.world = 1;
   g_comm.rank = 0;
 }
@@ -119,6 +125,20 @@ void comm_allgather_inplace(void* buf, size_t chunk_bytes, cudaStream_t s) {
   nccl_check(api().AllGather(base + (size_t)g_comm.rank * chunk_bytes, base, chunk_bytes, ncclChar,
                              static_cast<ncclComm_t>(g_comm.nccl), s),
              "ncclAllGather");
+}
+
+void comm_exchange_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cudaStream_t s) {
+  if (!g_comm.active() || d_lo > d_hi) return;
+  char* base = static_cast<char*>(buf);
+  int const P = g_comm.world, r = g_comm.rank;
+  ncclComm_t c = static_cast<ncclComm_t>(g_comm.nccl);
+  nccl_check(api().GroupStart(), "ncclGroupStart");
+  for (int d = d_lo; d <= d_hi; ++d) {
+    int const to = ((r - d) % P + P) % P, from = (r + d) % P;
+    nccl_check(api().Send(base + (size_t)r * chunk_bytes, chunk_bytes, ncclChar, to, c, s), "ncclSend");
+    nccl_check(api().Recv(base + (size_t)from * chunk_bytes, chunk_bytes, ncclChar, from, c, s), "ncclRecv");
+  }
+  nccl_check(api().GroupEnd(), "ncclGroupEnd");
 }
 
 void comm_allreduce_sum_f64(double* dev, size_t count, cudaStream_t s) {

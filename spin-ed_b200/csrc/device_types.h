@@ -109,23 +109,67 @@ struct MatvecParams {
 // inside a slice element j of lane l sits at slice_off[s] + 32 j + l, so a warp reads its
 // column indices with one coalesced 128-byte load per j.
 //
-// With more than one rank the elements of a row are stored in two classes: first those whose
-// source entry of x is owned by this rank (available before the all-gather of the Krylov vector
-// has delivered anything), then the remote ones.  Inside a slice the local class occupies slots
-// [0, wl) and the remote class [wl, width) for every lane, so both classes are read coalesced;
-// the streaming kernel runs once per class and the local pass overlaps the all-gather.
+// With more than one rank the elements of a row are stored in classes by where their source entry
+// of x lives: class 0 -- owned by this rank (available before the exchange of the Krylov vector
+// has delivered anything); class 1 -- owned by one of the `near` next ranks (first exchange round);
+// class 2 -- the other ranks (second round; absent when all peers fit in one round).  Inside a slice
+// class c occupies slots [start_c, start_c+1) for every lane, so every class is read coalesced; the
+// streaming kernel runs once per class, each pass overlapping the transfer the next one waits for.
+constexpr int kMaxClasses = 4;
+// Window class (optional, class 0 when present): a warp walks the 32 consecutive local rows of a
+// slice, and a fifth (6x6) to two fifths (chains) of their elements gather from local rows within
+// a few hundred rows of the slice itself.  The streaming kernel stages x[32 s - W, 32 s + 32 + W)
+// (local indices) in shared memory once per slice and serves these elements from there: a handful
+// of bank-conflict wavefronts instead of ~13 L1 lines per warp gather.  Their slots hold the offset
+// into the window instead of a position.
+constexpr u32 kWindow = 128;                     // W
+constexpr u32 kWindowEntries = 32 + 2 * kWindow;
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
-  u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
+  u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout);
+                         // window class: offset into the slice's window
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
-  dev_u16 const* len;    // [local rows] stored elements of the row (two classes: the local-source ones)
-  dev_u16 const* len_remote;  // [local rows] remote-source elements; null with one class
-  u32 const* slice_wl;   // [n_slices] slots of the local class per lane; null with one class
+  dev_u16 const* len;    // [2 * n_classes][local rows]: per source class the elements that carry the
+                         // default coefficient (no code is read for them), then the coded ones
+  u32 const* slice_start;  // [n_slices][3] first slot of classes 1, 2, 3; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
   int code_wide;         // 1: u16 codes
   u32 n_codes;           // entries of `table`
+  u32 n_classes;         // [window] local [remote near] [remote far]: 1 .. 4
+  u32 near;              // first remote class = owners rank+1 .. rank+near (mod world)
+  u32 default_code;      // the coefficient almost every element carries (first matrix value, chi = 1,
+                         // trivial stabiliser).  Inside its class region [start_c, start_c+1) a row keeps
+                         // these elements from the front, s = start_c + j, and the others -- with
+                         // their code -- from the back, s = start_c+1 - 1 - j ("two-ended"), so one
+                         // traversal fills both without knowing their numbers in advance.
+  u32 window;            // 1: class 0 is the window class
+  u32 rounds;            // exchange rounds = remote classes (0 with one rank)
+  u32 pad_;
 };
+
+// first remote class / classes handled by pass `phase` (0: all; 1: everything this rank owns the
+// sources of; 2, 3: first / second exchange round)
+SPED_DIST_FN u32 cache_first_remote(u32 window) { return window ? 2u : 1u; }
+
+// Class of the entry at position `pos` of the replicated vector for local row i of rank d.rank;
+// *window_offset receives the offset into the slice's window for the window class.
+SPED_DIST_FN u32 dist_source_class(RowDist const& d, u64 pos, u64 i, u32 window, u32 rounds, u32 near, u32* window_offset) {
+  u32 const owner = d.world == 1 ? 0u : (u32)(pos / d.chunk);
+  if (owner == d.rank) {
+    if (window) {
+      u64 const local = pos - (u64)d.rank * d.chunk;
+      u64 const off = local + kWindow - (i & ~(u64)31);  // wraps to a huge value when below the window
+      if (off < kWindowEntries) {
+        *window_offset = (u32)off;
+        return 0u;
+      }
+    }
+    return window ? 1u : 0u;
+  }
+  u32 const dd = owner > d.rank ? owner - d.rank : owner + d.world - d.rank;
+  return cache_first_remote(window) + ((rounds == 2 && dd > near) ? 1u : 0u);
+}
 
 struct FillParams {
   RowContext ctx;
@@ -133,11 +177,16 @@ struct FillParams {
   u64 const* slice_off;
   u32* idx;
   void* code;              // u8 or u16 per slot, see code_wide
-  dev_u16* len;
-  dev_u16* len_remote;     // two classes (see CacheView): remote-source count per row; else null
-  u32 const* slice_wl;     // two classes, fill pass: slots of the local class per slice; null in the count pass
-  int count_only;          // two classes, first pass: only len / len_remote are written
-  int pad0_;
+  dev_u16* len;            // [2 * n_classes][local rows] (see CacheView)
+  u32 default_code;
+  u32 pad1_;
+  u32 const* slice_start;  // several classes, fill pass: [n_slices][3] (see CacheView); null otherwise
+  int count_only;          // exact class sizes wanted: first pass, only `len` is written
+  u32 n_classes;
+  u32 near;
+  u32 window;              // see CacheView
+  u32 rounds;
+  u32 pad0_;
   dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
   dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
   dev_u16 const* pid_map;  // [denom] phase numerator -> id among the phases that occur (null: trivial group)

@@ -10,7 +10,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
-#include <map>
+#include <type_traits>
 #include <vector>
 
 #include "internal.h"
@@ -26,6 +26,7 @@ struct Dim1 { unsigned x, y, z; };
 static const Dim1 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 template <class T> static inline T __ldg(T const* p) { return *p; }
 static inline void __syncthreads() {}
+static inline void __syncwarp() {}
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
@@ -123,71 +124,6 @@ struct Problem {
   }
 };
 
-
-// Code maps of the operator cache -- the same construction as in Operator::cache_usable (opcache.cu).
-struct CodeMaps {
-  std::vector<double> values_re, values_im;
-  std::vector<std::uint16_t> hid_map, sid_map, sid_stab, pid_map, pid_phase;
-  u32 n_pid = 1;
-  u64 n_codes = 0;
-};
-char const* build_code_maps(Operator const& op, CodeMaps& out) {
-  Basis& b = *op.basis;
-  std::map<std::pair<double, double>, u32> seen;
-  for (auto const& t : op.terms) {
-    u32 dim = 1u << t.k;
-    for (u32 a = 0; a < dim; ++a)
-      for (u32 c = 0; c < dim; ++c) {
-        cplx v = t.matrix[a * dim + c];
-        u32 id = 0;
-        if (a != c && v != cplx(0, 0)) {
-          auto key = std::make_pair(v.real(), v.imag());
-          auto it = seen.find(key);
-          if (it == seen.end()) {
-            it = seen.emplace(key, (u32)out.values_re.size()).first;
-            out.values_re.push_back(v.real());
-            out.values_im.push_back(v.imag());
-          }
-          id = it->second;
-        }
-        out.hid_map.push_back((std::uint16_t)id);
-      }
-  }
-  if (out.values_re.empty()) return "operator is diagonal";
-  bool const sym = !b.trivial();
-  u64 const order = b.group_order();
-  out.sid_map.assign(order + 1, 0);
-  if (sym) {
-    for (u64 s = 1; s <= order; ++s)
-      if (order % s == 0) {
-        out.sid_map[s] = (std::uint16_t)out.sid_stab.size();
-        out.sid_stab.push_back((std::uint16_t)s);
-      }
-  } else {
-    out.sid_stab.push_back(1);
-  }
-  if (sym) {
-    u32 const D = (u32)b.group->denom;
-    std::vector<char> occurs(D, 0);
-    for (auto const& e : b.group->elems) {
-      occurs[(u32)e.phase % D] = 1;
-      if (b.spin_inversion < 0) occurs[((u32)e.phase + D / 2) % D] = 1;
-    }
-    out.pid_map.assign(D, 0);
-    for (u32 ph = 0; ph < D; ++ph)
-      if (occurs[ph]) {
-        out.pid_map[ph] = (std::uint16_t)out.pid_phase.size();
-        out.pid_phase.push_back((std::uint16_t)ph);
-      }
-  } else {
-    out.pid_phase.push_back(0);
-  }
-  out.n_pid = (u32)out.pid_phase.size();
-  out.n_codes = (u64)out.values_re.size() * out.n_pid * out.sid_stab.size();
-  if (out.n_codes > 65536) return "more than 65536 distinct coefficients";
-  return nullptr;
-}
-
 template <class T>
 void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* stats, u32 ncols, T* y_block) {
   RowDist const& d = pr.dist;
@@ -233,18 +169,24 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
     table[3 * c + 1] = vy;
     table[3 * c + 2] = pr.sym ? pr.norm_table[cm.sid_stab[sid]] : 1.0;
   }
-  bool const two = d.world > 1;  // local-source / remote-source classes
-  u32 const n_classes = two ? 2u : 1u;
+  u32 const rounds = (u32)exchange_rounds(d.world);
+  u32 const window = window_enabled() ? 1u : 0u;
+  u32 const n_classes = window + 1u + rounds;
+  u32 const near = exchange_near(d.world);
   bool const wide = cm.n_codes > 256;
   u64 const n_slices = (n_local + 31) / 32;
-  std::vector<std::uint16_t> len(std::max<u64>(n_local, 1), 0), len_remote(std::max<u64>(n_local, 1), 0);
-  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_wl(std::max<u64>(n_slices, 1), 0);
+  std::vector<std::uint16_t> len(std::max<u64>(n_local, 1) * 2 * n_classes, 0);
+  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_start(std::max<u64>(n_slices, 1) * 3, 0);
   int overflow = 0;
   FillParams fp{};
   fp.ctx = pr.ctx;
   fp.terms = pr.terms;
   fp.len = len.data();
-  fp.len_remote = two ? len_remote.data() : nullptr;
+  fp.n_classes = n_classes;
+  fp.near = near;
+  fp.window = window;
+  fp.rounds = rounds;
+  fp.default_code = cm.default_code;
   fp.hid_map = cm.hid_map.data();
   fp.sid_map = pr.sym ? cm.sid_map.data() : nullptr;
   fp.pid_map = pr.sym ? cm.pid_map.data() : nullptr;
@@ -252,20 +194,20 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   fp.n_sid = n_sid;
   fp.code_wide = wide ? 1 : 0;
   fp.overflow = &overflow;
-  if (two) {
+  if (rounds > 0) {  // several ranks: exact class sizes from a counting traversal
     fp.count_only = 1;
     pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
     for (u64 s = 0; s < n_slices; ++s) {  // class_width_kernel
-      u32 wl = 0, wr = 0;
-      for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i) {
-        wl = std::max<u32>(wl, len[i]);
-        wr = std::max<u32>(wr, len_remote[i]);
-      }
-      widths[s] = wl + wr;
-      slice_wl[s] = wl;
+      u32 w[kMaxClasses] = {0, 0, 0, 0};
+      for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i)
+        for (u32 c = 0; c < n_classes; ++c) w[c] = std::max<u32>(w[c], len[(u64)(2 * c) * n_local + i]);
+      widths[s] = w[0] + w[1] + w[2] + w[3];
+      slice_start[3 * s] = w[0];
+      slice_start[3 * s + 1] = w[0] + w[1];
+      slice_start[3 * s + 2] = w[0] + w[1] + w[2];
     }
     fp.count_only = 0;
-    fp.slice_wl = slice_wl.data();
+    fp.slice_start = slice_start.data();
   } else {
     for (u64 s = 0; s < n_slices; ++s) {  // slice_width_kernel: cheap upper bound
       u32 mx = 0;
@@ -279,8 +221,13 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
         }
         mx = std::max(mx, ub);
       }
-      widths[s] = mx;
+      u32 const ws = window ? window_slots() : 0u;  // guessed width of the window region
+      widths[s] = mx + ws;
+      slice_start[3 * s] = ws;
+      slice_start[3 * s + 1] = mx + ws;
+      slice_start[3 * s + 2] = mx + ws;
     }
+    if (window) fp.slice_start = slice_start.data();
   }
   std::vector<u64> slice_off(n_slices + 1, 0);
   for (u64 s = 0; s < n_slices; ++s) slice_off[s + 1] = slice_off[s] + 32ull * widths[s];
@@ -291,23 +238,27 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   fp.idx = idx.data();
   fp.code = code.data();
   std::fill(len.begin(), len.end(), 0);
-  std::fill(len_remote.begin(), len_remote.end(), 0);
   pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
   if (overflow) fail(SPED_INTERNAL_ERROR, "emulated cache fill: a row exceeded its slot bound");
-  u64 elements = 0, local_elements = 0;
-  for (u64 i = 0; i < n_local; ++i) {
-    elements += len[i] + (two ? len_remote[i] : 0);
-    local_elements += len[i];
-  }
+  u64 elements = 0, dflt = 0;
+  for (u32 seg = 0; seg < 2 * n_classes; ++seg)
+    for (u64 i = 0; i < n_local; ++i) {
+      elements += len[(u64)seg * n_local + i];
+      if (!(seg & 1)) dflt += len[(u64)seg * n_local + i];
+    }
+  u64 windowed = 0;
+  if (window)
+    for (u64 i = 0; i < n_local; ++i) windowed += len[i] + len[n_local + i];
   stats[0] = slots;
   stats[1] = elements;
-  stats[2] = local_elements;
+  stats[2] = dflt;
   stats[3] = n_classes;
+  stats[4] = windowed;
 
   // ---- streaming kernel: all classes in one pass, then class by class ----
   CachedParams cp{};
-  cp.cache = CacheView{slice_off.data(), idx.data(), code.data(), len.data(), two ? len_remote.data() : nullptr,
-                       two ? slice_wl.data() : nullptr, table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes};
+  cp.cache = CacheView{slice_off.data(), idx.data(), code.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,
+                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, window, rounds, 0u};
   cp.ctx = pr.ctx;
   cp.diag_re = pr.diag_re.data();
   cp.diag_im = cplx_diag ? pr.diag_im.data() : nullptr;
@@ -328,21 +279,31 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   };
   if (n_local) {
     launch(y_all, 0);
-    for (u32 c = 0; c < n_classes; ++c) launch(y_phased, 1 + (int)c);
+    for (u32 ph = 1; ph <= 1 + rounds; ++ph) launch(y_phased, (int)ph);  // local pass, then one pass per exchange round
   }
-  // ---- several columns at once (NB = 4 variant): column c is x shifted cyclically by c rows ----
+  // ---- block kernel: columns c > 0 are x shifted cyclically by c rows (in global order) ----
   if (ncols > 1 && n_local) {
     std::vector<T> xcols(padded * ncols, T{});
     for (u32 c = 0; c < ncols; ++c)
       for (u64 g = 0; g < d.n; ++g) xcols[(u64)c * padded + dist_global_to_pos(d, g)] = x_global[(g + c) % d.n];
-    cp.x = xcols.data();
+    u32 const nb = ncols == 2 ? 2u : 4u;
+    std::vector<T> xt(padded * nb, T{});
+    if (nb == 2) interleave_kernel<T, 2>(xcols.data(), padded, ncols, padded, xt.data());
+    else interleave_kernel<T, 4>(xcols.data(), padded, ncols, padded, xt.data());
+    cp.x = xt.data();
     cp.y = y_block;
     cp.ncols = ncols;
     cp.phase = 0;
-    if (wide && pr.sym) cached_matvec_kernel<T, 4, std::uint16_t, true, false, 8>(cp);
-    else if (wide) cached_matvec_kernel<T, 4, std::uint16_t, false, false, 8>(cp);
-    else if (pr.sym) cached_matvec_kernel<T, 4, std::uint8_t, true, false, 8>(cp);
-    else cached_matvec_kernel<T, 4, std::uint8_t, false, false, 8>(cp);
+    auto go = [&](auto nbtag) {
+      constexpr int NB = decltype(nbtag)::value;
+      constexpr int U = NB == 2 ? 8 : 4;
+      if (wide && pr.sym) cached_block_kernel<T, NB, std::uint16_t, true, U>(cp);
+      else if (wide) cached_block_kernel<T, NB, std::uint16_t, false, U>(cp);
+      else if (pr.sym) cached_block_kernel<T, NB, std::uint8_t, true, U>(cp);
+      else cached_block_kernel<T, NB, std::uint8_t, false, U>(cp);
+    };
+    if (nb == 2) go(std::integral_constant<int, 2>());
+    else go(std::integral_constant<int, 4>());
   }
 }
 

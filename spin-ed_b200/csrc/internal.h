@@ -125,6 +125,7 @@ struct Comm {
   cudaStream_t stream = nullptr;
   cudaStream_t gather_stream = nullptr;           // the all-gather of a sharded matvec runs here ...
   cudaEvent_t ev_ready = nullptr, ev_gathered = nullptr;  // ... between these two events
+  cudaEvent_t ev_round1 = nullptr;                // end of the first exchange round (three source classes)
   bool active() const { return world > 1; }
 };
 Comm& comm();
@@ -133,6 +134,9 @@ void comm_init(int world, int rank, void const* id128);
 void comm_finalize();
 // in-place all-gather: every rank owns chunk `rank` of `chunk_bytes` inside buf (P chunks)
 void comm_allgather_inplace(void* buf, size_t chunk_bytes, cudaStream_t s);
+// one round of the shard exchange: this rank's chunk goes to ranks rank-d and the chunks of ranks
+// rank+d arrive in place, for d in [d_lo, d_hi] (mod world); grouped NCCL send/recv
+void comm_exchange_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cudaStream_t s);
 void comm_allreduce_sum_f64(double* dev, size_t count, cudaStream_t s);
 void comm_allreduce_sum_u64(unsigned long long* dev, size_t count, cudaStream_t s);
 void comm_broadcast_bytes(void* dev, size_t bytes, int root, cudaStream_t s);
@@ -204,6 +208,7 @@ struct Operator {
   DeviceBuffer<unsigned char> d_terms;  // packed bonds + matrices (see operator.cu)
   DeviceBuffer<double> d_diag;          // local rows (real part) [+ imaginary part if !real_diagonal]
   DeviceBuffer<unsigned char> stage_x, stage_y;  // grow-only device staging of the host-pointer entry
+  DeviceBuffer<unsigned char> block_x;           // grow-only: interleaved copy of a block of vectors (opcache.cu)
 
   // operator cache (opcache.cu): off-diagonal elements of the local rows resident in HBM
   int cache_mode = -1;        // -1: auto (build when it fits), 0: never, 1: always try
@@ -213,17 +218,18 @@ struct Operator {
   DeviceBuffer<u32> c_idx;
   DeviceBuffer<unsigned char> c_code;  // u8 or u16 per slot
   int c_code_wide = 0;
-  DeviceBuffer<std::uint16_t> c_len, c_len_remote;  // per row: stored elements (two classes: local / remote sources)
-  DeviceBuffer<u32> c_slice_wl;                     // two classes: slots of the local class per slice
+  DeviceBuffer<std::uint16_t> c_len;   // [2 * c_classes][local rows]: default-coefficient / coded elements per source class
+  DeviceBuffer<u32> c_slice_start;     // [slices][3] first slot of classes 1, 2, 3 (several classes only)
+  u32 c_classes = 1, c_near = 0, c_default_code = 0, c_window = 0, c_rounds = 0;
   DeviceBuffer<double> c_table;
   u64 c_slices = 0, c_slots = 0, cache_bytes = 0;
   double cache_build_seconds = 0;
   bool cache_usable();        // true once the cache is (or has just been) built
   void drop_cache();
   // local rows [row_lo, row_hi) only (row_lo a multiple of 32); y is still indexed by local row
-  // phase: 0 all, 1 diagonal + local-source class, 2 += remote-source class (two-class cache, world > 1)
+  // phase: 0 all classes, 1 + c: source class c only (class 0 starts from the diagonal, later ones add to y)
   void cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo = 0,
-                     u64 row_hi = ~(u64)0, int phase = 0);
+                     u64 row_hi = ~(u64)0, int phase = 0, bool beside_transfer = false);
   // y_local = H x for one column given only this rank's shard of x: all-gather into `xfull`
   // ([rank][local] layout, world * chunk entries) overlapped with the local-source pass
   void matvec_sharded(int dtype, void const* x_local, void* y_local, void* xfull, cudaStream_t s);
@@ -249,6 +255,19 @@ struct Operator {
   void count_elements(u64& rows, u64& offdiag);
 };
 
+int exchange_rounds(unsigned world);  // opcache.cu
+unsigned exchange_near(unsigned world);
+bool window_enabled();                // opcache.cu
+unsigned window_slots();
+
+// Code maps of the operator cache (opcache.cu, build_code_maps)
+struct CodeMaps {
+  std::vector<double> values_re, values_im;                            // distinct off-diagonal matrix values
+  std::vector<std::uint16_t> hid_map, sid_map, sid_stab, pid_map, pid_phase;
+  u32 n_pid = 1, default_code = 0;
+  u64 n_codes = 0;
+};
+char const* build_code_maps(Operator const& op, CodeMaps& out);
 // host copy of the packed terms (operator.cu): bonds in the order the kernels visit them
 void packed_terms_host(std::vector<Interaction> const& terms, std::vector<DevBond>& bonds, std::vector<double>& pool_re,
                        std::vector<double>& pool_im, std::vector<std::uint16_t>& masks);

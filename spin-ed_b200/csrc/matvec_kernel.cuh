@@ -55,24 +55,28 @@ template <> struct Traits<float> {
   typedef double Acc;
   static constexpr bool cplx = false;
   static __device__ __forceinline__ Acc load(float const* p) { return (double)__ldg(p); }
+  static __device__ __forceinline__ Acc to_acc(float v) { return (double)v; }
   static __device__ __forceinline__ void store(float* p, Acc v) { *p = (float)v; }
 };
 template <> struct Traits<double> {
   typedef double Acc;
   static constexpr bool cplx = false;
   static __device__ __forceinline__ Acc load(double const* p) { return __ldg(p); }
+  static __device__ __forceinline__ Acc to_acc(double v) { return v; }
   static __device__ __forceinline__ void store(double* p, Acc v) { *p = v; }
 };
 template <> struct Traits<float2> {
   typedef double2 Acc;
   static constexpr bool cplx = true;
   static __device__ __forceinline__ Acc load(float2 const* p) { float2 v = __ldg(p); return make_double2(v.x, v.y); }
+  static __device__ __forceinline__ Acc to_acc(float2 v) { return make_double2(v.x, v.y); }
   static __device__ __forceinline__ void store(float2* p, Acc v) { *p = make_float2((float)v.x, (float)v.y); }
 };
 template <> struct Traits<double2> {
   typedef double2 Acc;
   static constexpr bool cplx = true;
   static __device__ __forceinline__ Acc load(double2 const* p) { return __ldg(p); }
+  static __device__ __forceinline__ Acc to_acc(double2 v) { return v; }
   static __device__ __forceinline__ void store(double2* p, Acc v) { *p = v; }
 };
 
@@ -212,7 +216,7 @@ __device__ __forceinline__ void matvec_rows(MatvecParams const& p, TermsView con
 
 // Fills the operator cache: the same traversal as matvec_rows, but instead of gathering x the
 // (target index, coefficient code) of every element that exists is written to its slot.  With
-// two classes (CacheView) a first pass with count_only set sizes the classes.
+// several classes (CacheView) a first pass with count_only set sizes the classes.
 // Consecutive local rows map to consecutive lanes (blockDim and the grid stride are multiples of
 // 32), so a warp owns exactly one slice at a time.
 template <class Canon>
@@ -221,21 +225,22 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
   BasisIndex const ix = p.ctx.index;
   RowDist const dist = p.ctx.dist;
   u64 const n_local = dist.n_local;
-  bool const two = p.len_remote != nullptr;      // local-source / remote-source classes (world > 1)
   bool const count_only = p.count_only != 0;
-  u64 const self0 = (u64)dist.rank * dist.chunk;
+  u32 const nc = p.n_classes;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
     u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 base = 0;
-    u32 width = 0, wl = 0;
+    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u, 0u};  // first slot of each class; start[c >= n_classes] = width
     if (!count_only) {
       base = __ldg(p.slice_off + slice) + (i & 31);
-      width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
-      wl = two ? __ldg(p.slice_wl + slice) : width;
+      u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
+      for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(p.slice_start + 3 * slice + (c - 1)) : width;
     }
-    u32 jl = 0, jr = 0;
+    // per class: cd = elements with the default coefficient (stored from the front of the class
+    // region), cx = coded elements (stored from its back)
+    u32 cd[kMaxClasses] = {0u, 0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -243,29 +248,39 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
-      bool const local = !two || (pos - self0 < dist.chunk);
-      if (count_only) {
-        if (local) ++jl; else ++jr;
-        return;
-      }
-      u32 slot;
-      if (local) {
-        if (jl >= wl) { *p.overflow = 1; return; }
-        slot = jl++;
-      } else {
-        if (wl + jr >= width) { *p.overflow = 1; return; }
-        slot = wl + jr++;
-      }
+      u32 woff = 0;
+      u32 cls = dist_source_class(dist, pos, i, p.window, p.rounds, p.near, &woff);
+      // a full window region (its width is a guess when the classes are not counted first) sends
+      // the element to the plain local class, where every local source can live
+      if (!count_only && cls == 0 && p.window && cd[0] + cx[0] >= start[1] - start[0]) cls = 1;
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
       u32 const code = (hid * p.denom + pid) * p.n_sid + sid;
-      p.idx[base + (u64)slot * 32] = (u32)pos;
-      if (p.code_wide) static_cast<dev_u16*>(p.code)[base + (u64)slot * 32] = (dev_u16)code;
-      else static_cast<dev_u8*>(p.code)[base + (u64)slot * 32] = (dev_u8)code;
+      bool const dflt = code == p.default_code;
+      u32 const nd = cd[cls], nx = cx[cls];
+      if (dflt) ++cd[cls]; else ++cx[cls];
+      if (count_only) return;
+      u32 const lo = start[cls], hi = start[cls + 1];
+      if (lo + nd + nx >= hi) {  // the two ends would meet
+        *p.overflow = 1;
+        return;
+      }
+      u64 const at = base + (u64)(dflt ? lo + nd : hi - 1u - nx) * 32;
+      p.idx[at] = (cls == 0 && p.window) ? woff : (u32)pos;
+      if (!dflt) {
+        if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
+        else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
+      }
     });
-    p.len[i] = (dev_u16)jl;
-    if (two) p.len_remote[i] = (dev_u16)jr;
+    for (u32 c = 0; c < nc; ++c) {
+      if (count_only) {  // class sizes only: the width pass needs cd + cx per class
+        p.len[(u64)(2 * c) * n_local + i] = (dev_u16)(cd[c] + cx[c]);
+      } else {
+        p.len[(u64)(2 * c) * n_local + i] = (dev_u16)cd[c];
+        p.len[(u64)(2 * c + 1) * n_local + i] = (dev_u16)cx[c];
+      }
+    }
   }
 }
 

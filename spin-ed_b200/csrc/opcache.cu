@@ -5,13 +5,15 @@
 //
 // The reference recomputes every matrix element in every ls_operator_matmat call
 // (/root/reference/src/SpinED/Internal.hs:411-429 is called once per PRIMME block per iteration).
-// Results are bit-identical to the matrix-free kernel: same elements, same order, and the
-// coefficient is rebuilt from the same factors,  w = v * (norm_s * (1 / norm_r)).
+// Results agree with the matrix-free kernel to rounding: same elements and the same coefficient
+// factors, w = v * (norm_s * (1 / norm_r)), but the elements that carry the default coefficient
+// (first matrix value, chi = 1, trivial stabiliser: almost all of them) are stored first, without a
+// code, and their x entries are summed before the one multiplication.
 //
-// Layout (sliced ELL): rows in slices of 32 = one warp; element j of lane l of slice s is at
-// slice_off[s] + 32 j + l.  Column indices are u32 (N < 2^32), coefficient codes u8 (u16 when there
-// are more than 256 distinct (value, phase, stabiliser) triples) into a table of (Re v, Im v,
-// norm_s), v = M[a][b] * chi(g').  5 or 6 bytes per element.
+// Layout (sliced ELL): rows in slices of 32 = one warp; slot j of lane l of slice s is at
+// slice_off[s] + 32 j + l.  Positions are u32 (N < 2^32); coded elements carry a u8 code (u16 when
+// there are more than 256 distinct (value, phase, stabiliser) triples) into a table of
+// (Re v, Im v, norm_s), v = M[a][b] * chi(g').  4 bytes per default element, 5 or 6 per coded one.
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -29,7 +31,8 @@ namespace {
 
 // Upper bound of the row lengths (transitions with a non-zero matrix element, whether or not the
 // target survives the projection) and its maximum over each slice.
-__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths) {
+__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths, u32 window_slots,
+                                                               u32* slice_start) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(terms_g, smem);
   u64 const n_local = ctx.dist.n_local;
@@ -47,21 +50,36 @@ __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, T
       }
     }
     u32 mx = __reduce_max_sync(0xffffffffu, ub);
-    if ((i & 31) == 0) widths[i >> 5] = mx;
+    if ((i & 31) == 0) {
+      // window class in front (its width is a guess: what does not fit goes to the local class,
+      // which is wide enough for every element of the row), then the local class
+      widths[i >> 5] = mx + window_slots;
+      if (slice_start) {
+        slice_start[3 * (i >> 5)] = window_slots;
+        slice_start[3 * (i >> 5) + 1] = mx + window_slots;
+        slice_start[3 * (i >> 5) + 2] = mx + window_slots;
+      }
+    }
   }
 }
 
-// Two classes: per slice the local class takes wl = max lenL slots per lane, the remote class
-// max lenR; widths[s] = wl + wr.
-__global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len_local, std::uint16_t const* len_remote,
-                                                               u64 n_local, u32* widths, u32* slice_wl) {
+// Several classes: per slice class c takes max_lanes len_c slots per lane; widths[s] is their sum
+// and slice_start[s] = first slot of classes 1, 2, 3.
+__global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len, u64 n_local, u32 n_classes,
+                                                               u32* widths, u32* slice_start) {
   u64 const n_padded = (n_local + 31) & ~(u64)31;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
-    u32 l = i < n_local ? len_local[i] : 0u, r = i < n_local ? len_remote[i] : 0u;
-    u32 wl = __reduce_max_sync(0xffffffffu, l), wr = __reduce_max_sync(0xffffffffu, r);
+    u32 w[kMaxClasses] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (u32 c = 0; c < (u32)kMaxClasses; ++c) {
+      u32 v = (c < n_classes && i < n_local) ? len[(u64)(2 * c) * n_local + i] : 0u;  // count pass: class totals
+      w[c] = __reduce_max_sync(0xffffffffu, v);
+    }
     if ((i & 31) == 0) {
-      widths[i >> 5] = wl + wr;
-      slice_wl[i >> 5] = wl;
+      widths[i >> 5] = w[0] + w[1] + w[2] + w[3];
+      slice_start[3 * (i >> 5)] = w[0];
+      slice_start[3 * (i >> 5) + 1] = w[0] + w[1];
+      slice_start[3 * (i >> 5) + 2] = w[0] + w[1] + w[2];
     }
   }
 }
@@ -158,10 +176,10 @@ void launch_cached_kernel(CachedParams const& p, cudaStream_t s) {
     return std::max(n, 1);
   }();
   int grid = persistent_grid(p.row_hi - p.row_lo, kThreads, per_sm);
-  // The local-source pass runs beside NCCL's all-gather kernel: short-lived blocks (four rows per
-  // thread) keep freeing SM resources, so the gather's CTAs -- launched on a higher-priority
+  // A pass that runs beside one of NCCL's transfer kernels uses short-lived blocks (four rows per
+  // thread): they keep freeing SM resources, so the transfer's CTAs -- launched on a higher-priority
   // stream -- become resident at once instead of waiting for a persistent wave to drain.
-  if (p.phase == kPhaseLocal) grid = (int)std::min<u64>(((p.row_hi - p.row_lo) + 4 * kThreads - 1) / (4 * kThreads), 1u << 30);
+  if (p.beside_transfer) grid = (int)std::min<u64>(((p.row_hi - p.row_lo) + 4 * kThreads - 1) / (4 * kThreads), 1u << 30);
   Kernel<<<std::max(grid, 1), kThreads, 0, s>>>(p);
 }
 
@@ -184,18 +202,33 @@ void launch_cached_nb(CachedParams const& p, cudaStream_t s) {
   else launch_cached_variant<T, NB, std::uint8_t, false>(p, s);
 }
 
+template <class T, int NB>
+void launch_block(CachedParams const& p, T const* x, u64 xs, u64 n_entries, T* scratch, cudaStream_t s) {
+  interleave_kernel<T, NB><<<persistent_grid(n_entries, kThreads, 8), kThreads, 0, s>>>(x, xs, p.ncols, n_entries, scratch);
+  KERNEL_LAUNCHED();
+  CachedParams q = p;
+  q.x = scratch;
+  constexpr int U = NB == 2 ? 8 : 4;  // 32 accumulator-typed values in flight either way
+  bool const wide = p.cache.code_wide != 0, sym = p.sym != 0;
+  if (wide && sym) launch_cached_kernel<cached_block_kernel<T, NB, std::uint16_t, true, U>>(q, s);
+  else if (wide) launch_cached_kernel<cached_block_kernel<T, NB, std::uint16_t, false, U>>(q, s);
+  else if (sym) launch_cached_kernel<cached_block_kernel<T, NB, std::uint8_t, true, U>>(q, s);
+  else launch_cached_kernel<cached_block_kernel<T, NB, std::uint8_t, false, U>>(q, s);
+}
+
+// `scratch` holds the interleaved copy of up to four columns (n_entries * 4 values)
 template <class T>
-void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, cudaStream_t s) {
+void launch_cached(CachedParams p, u64 block, u64 xs, u64 ys, u64 n_entries, void* scratch, cudaStream_t s) {
   T const* x = static_cast<T const*>(p.x);
   T* y = static_cast<T*>(p.y);
   for (u64 c0 = 0; c0 < block;) {
     u64 left = block - c0;
     p.x = x + c0 * xs;
     p.y = y + c0 * ys;
-    bool wide = left > 1;
-    p.ncols = (u32)std::min<u64>(left, wide ? 4 : 1);
-    if (wide) launch_cached_nb<T, 4>(p, s);
-    else launch_cached_nb<T, 1>(p, s);
+    p.ncols = (u32)std::min<u64>(left, 4);
+    if (p.ncols == 1) launch_cached_nb<T, 1>(p, s);
+    else if (p.ncols == 2) launch_block<T, 2>(p, x + c0 * xs, xs, n_entries, static_cast<T*>(scratch), s);
+    else launch_block<T, 4>(p, x + c0 * xs, xs, n_entries, static_cast<T*>(scratch), s);
     KERNEL_LAUNCHED();
     c0 += p.ncols;
   }
@@ -217,40 +250,25 @@ int env_cache_mode() {
 
 }  // namespace
 
-void Operator::drop_cache() {
-  cache_ready = false;
-  cache_rejected = false;
-  c_slice_off.release();
-  c_idx.release();
-  c_code.release();
-  c_len.release();
-  c_len_remote.release();
-  c_slice_wl.release();
-  c_table.release();
-  c_slices = c_slots = cache_bytes = 0;
+// Number of exchange rounds of a sharded matvec (and remote source classes of the cache): a function
+// of the world size and the environment only, so that every rank makes the same choice.
+// SPED_REMOTE_GROUPS=1: one round (NCCL all-gather) even with more than two ranks.
+int exchange_rounds(unsigned world) {
+  if (world <= 1) return 0;
+  char const* e = std::getenv("SPED_REMOTE_GROUPS");
+  return (world == 2 || (e && e[0] == '1')) ? 1 : 2;
 }
 
-// Builds the cache on first use when allowed and when it fits; afterwards just reports it.
-bool Operator::cache_usable() {
-  if (cache_ready) return true;
-  int mode = cache_mode >= 0 ? cache_mode : env_cache_mode();
-  if (mode == 0 || cache_rejected) return false;
-  Basis& b = *basis;
-  auto reject = [&](char const* why) {
-    SPED_LOG("operator cache not used: %s", why);
-    cache_rejected = true;
-    drop_cache();
-    cache_rejected = true;
-    return false;
-  };
-  if (dist.chunk * dist.world >= 0xffffffffull) return reject("replicated vector longer than 2^32 - 1 entries");
-  u64 const n_local = dist.n_local;
-  if (n_local == 0) return false;
-  auto t0 = std::chrono::steady_clock::now();
-
+// Coefficient codes of the operator cache: code = (hid * n_pid + pid) * n_sid + sid with hid the
+// distinct off-diagonal matrix value, pid the phase numerator (among those that occur in G') and
+// sid the stabiliser size of the target (a divisor of |G'|).  Returns null, or why there can be no
+// cache.  Host only; shared with the host emulation of the kernels (emul.cpp).
+char const* build_code_maps(Operator const& op, CodeMaps& out) {
   // distinct off-diagonal matrix values -> hid; stabiliser sizes -> sid
-  std::vector<double> values_re, values_im;
-  std::vector<std::uint16_t> hid_map;
+  std::vector<double>&values_re = out.values_re, &values_im = out.values_im;
+  std::vector<std::uint16_t>& hid_map = out.hid_map;
+  auto const& terms = op.terms;
+  Basis& b = *op.basis;
   {
     std::map<std::pair<double, double>, u32> seen;
     for (auto const& t : terms) {
@@ -273,10 +291,11 @@ bool Operator::cache_usable() {
         }
     }
   }
-  if (values_re.empty()) return reject("operator is diagonal");
+  if (values_re.empty()) return "operator is diagonal";
   bool const sym = !b.trivial();
   u64 const order = b.group_order();
-  std::vector<std::uint16_t> sid_map(order + 1, 0), sid_stab;
+  std::vector<std::uint16_t>&sid_map = out.sid_map, &sid_stab = out.sid_stab;
+  sid_map.assign(order + 1, 0);
   if (sym) {
     for (u64 s = 1; s <= order; ++s)
       if (order % s == 0) {
@@ -287,10 +306,10 @@ bool Operator::cache_usable() {
     sid_stab.push_back(1);
   }
   // phase numerators that some element of G' carries (the canonicalisation never reports others)
-  std::vector<std::uint16_t> pid_map, pid_phase;
+  std::vector<std::uint16_t>&pid_map = out.pid_map, &pid_phase = out.pid_phase;
   if (sym) {
     u32 const D = (u32)b.group->denom;
-    if (D > 65535) return reject("more than 65535 distinct phases");
+    if (D > 65535) return "more than 65535 distinct phases";
     std::vector<char> occurs(D, 0);
     for (auto const& e : b.group->elems) {
       occurs[(u32)e.phase % D] = 1;
@@ -305,9 +324,75 @@ bool Operator::cache_usable() {
   } else {
     pid_phase.push_back(0);
   }
-  u32 const n_pid = (u32)pid_phase.size();
-  u64 const n_codes = (u64)values_re.size() * n_pid * sid_stab.size();
-  if (n_codes > 65536) return reject("more than 65536 distinct coefficients");
+  u32 const n_pid = out.n_pid = (u32)pid_phase.size();
+  u64 const n_codes = out.n_codes = (u64)values_re.size() * n_pid * sid_stab.size();
+  if (n_codes > 65536) return "more than 65536 distinct coefficients";
+
+  // the coefficient almost every element carries: first off-diagonal value, chi = 1, trivial stabiliser
+  out.default_code = ((0u * n_pid + (sym ? (u32)pid_map[0] : 0u)) * (u32)sid_stab.size()) + (sym ? (u32)sid_map[1] : 0u);
+  if (char const* e = std::getenv("SPED_DEFAULT_CLASS"))
+    if (e[0] == '0') out.default_code = ~0u;  // tuning / diagnosis: no element matches, everything is stored coded
+  return nullptr;
+}
+
+// SPED_WINDOW=0 switches the window class off; SPED_WINDOW_SLOTS sets its width per lane when the
+// classes are not counted first (one rank): window-eligible elements beyond it go to the local class.
+bool window_enabled() {
+  char const* e = std::getenv("SPED_WINDOW");
+  return !(e && e[0] == '0');
+}
+unsigned window_slots() {
+  char const* e = std::getenv("SPED_WINDOW_SLOTS");
+  int v = e && *e ? std::atoi(e) : 16;
+  return (unsigned)std::max(1, std::min(v, 64));
+}
+
+// Peers of the first exchange round: ranks r+1 .. r+near (a function of the world size and the
+// environment only, like exchange_rounds: every rank must agree on who talks in which round).
+unsigned exchange_near(unsigned world) { return exchange_rounds(world) == 2 ? world / 2 : world - 1; }
+
+void Operator::drop_cache() {
+  cache_ready = false;
+  cache_rejected = false;
+  c_slice_off.release();
+  c_idx.release();
+  c_code.release();
+  c_len.release();
+  c_slice_start.release();
+  c_classes = 1;
+  c_near = 0;
+  c_window = 0;
+  c_rounds = 0;
+  c_table.release();
+  c_slices = c_slots = cache_bytes = 0;
+}
+
+// Builds the cache on first use when allowed and when it fits; afterwards just reports it.
+bool Operator::cache_usable() {
+  if (cache_ready) return true;
+  int mode = cache_mode >= 0 ? cache_mode : env_cache_mode();
+  if (mode == 0 || cache_rejected) return false;
+  Basis& b = *basis;
+  auto reject = [&](char const* why) {
+    SPED_LOG("operator cache not used: %s", why);
+    cache_rejected = true;
+    drop_cache();
+    cache_rejected = true;
+    return false;
+  };
+  if (dist.chunk * dist.world >= 0xffffffffull) return reject("replicated vector longer than 2^32 - 1 entries");
+  u64 const n_local = dist.n_local;
+  if (n_local == 0) return false;
+  auto t0 = std::chrono::steady_clock::now();
+
+  CodeMaps cm_;
+  if (char const* why = build_code_maps(*this, cm_)) return reject(why);
+  std::vector<double>&values_re = cm_.values_re, &values_im = cm_.values_im;
+  std::vector<std::uint16_t>&hid_map = cm_.hid_map, &sid_map = cm_.sid_map, &sid_stab = cm_.sid_stab, &pid_map = cm_.pid_map,
+                           &pid_phase = cm_.pid_phase;
+  bool const sym = !b.trivial();
+  u32 const n_pid = cm_.n_pid;
+  u64 const n_codes = cm_.n_codes;
 
   // maps and coefficient table
   DeviceBuffer<double> d_vre, d_vim;
@@ -329,18 +414,28 @@ bool Operator::cache_usable() {
   c_slices = (n_local + 31) / 32;
   c_code_wide = n_codes > 256 ? 1 : 0;
   u64 const code_bytes = c_code_wide ? 2 : 1;
-  bool const two = dist.world > 1;  // local-source / remote-source classes (see CacheView)
+  // source classes (see CacheView): local / peers of the first exchange round / of the second
+  u32 const world = dist.world;
+  c_rounds = (u32)exchange_rounds(world);
+  c_window = window_enabled() ? 1u : 0u;
+  c_classes = c_window + 1 + c_rounds;
+  c_near = exchange_near(world);  // 8 ranks: 4 peers in the first round, 3 in the second
+  bool const two = c_rounds > 0;  // several ranks: exact class sizes from a counting traversal
   MatvecParams mp = operator_params(*this);
   size_t tsm = terms_smem_bytes(mp.terms, false);
-  c_len.alloc(n_local);
-  if (two) c_len_remote.alloc(n_local);
+  c_len.alloc(n_local * 2 * c_classes);
   DeviceBuffer<int> d_flag(1);
   CUDA_CHECK(cudaMemset(d_flag.ptr, 0, sizeof(int)));
   FillParams fp{};
   fp.ctx = mp.ctx;
   fp.terms = mp.terms;
   fp.len = c_len.ptr;
-  fp.len_remote = two ? c_len_remote.ptr : nullptr;
+  fp.n_classes = c_classes;
+  fp.near = c_near;
+  fp.window = c_window;
+  fp.rounds = c_rounds;
+  c_default_code = cm_.default_code;
+  fp.default_code = c_default_code;
   fp.hid_map = d_hid.ptr;
   fp.sid_map = sym ? d_sid_map.ptr : nullptr;
   fp.pid_map = sym ? d_pid_map.ptr : nullptr;
@@ -380,14 +475,20 @@ bool Operator::cache_usable() {
   if (two) {
     fp.count_only = 1;
     launch_fill();
-    c_slice_wl.alloc(c_slices);
-    class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, c_len_remote.ptr, n_local,
-                                                                                 d_widths.ptr, c_slice_wl.ptr);
+    c_slice_start.alloc(c_slices * 3);
+    class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, d_widths.ptr,
+                                                                                 c_slice_start.ptr);
     fp.count_only = 0;
-    fp.slice_wl = c_slice_wl.ptr;
+    fp.slice_start = c_slice_start.ptr;
   } else {
     if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
+    if (c_window) {
+      c_slice_start.alloc(c_slices * 3);
+      fp.slice_start = c_slice_start.ptr;
+    }
+    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr,
+                                                                                 c_window ? window_slots() : 0u,
+                                                                                 c_window ? c_slice_start.ptr : nullptr);
   }
   KERNEL_LAUNCHED();
   c_slice_off.alloc(c_slices + 1);
@@ -395,7 +496,7 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * (4 + code_bytes) + n_local * (two ? 4 : 2) + (c_slices + 1) * (two ? 12 : 8) + n_codes * 24;
+  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 20 : 8) + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
@@ -423,17 +524,13 @@ bool Operator::cache_usable() {
 void Operator::cached_count(unsigned long long* d_out) {
   u64 n_local = dist.n_local;
   if (!n_local) return;
-  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local, d_out);
+  sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len.ptr, n_local * 2 * c_classes, d_out);
   KERNEL_LAUNCHED();
-  if (c_len_remote.ptr) {
-    sum_len_kernel<<<persistent_grid(n_local, kThreads, 4), kThreads>>>(c_len_remote.ptr, n_local, d_out);
-    KERNEL_LAUNCHED();
-  }
   CUDA_CHECK(cudaGetLastError());
 }
 
 void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo,
-                             u64 row_hi, int phase) {
+                             u64 row_hi, int phase, bool beside_transfer) {
   static bool const fetch_set = [] {  // tuning knob: DRAM->L2 fetch granularity (32, 64 or 128 bytes)
     char const* e = std::getenv("SPED_L2_FETCH");
     if (e && *e) {
@@ -448,9 +545,10 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   Basis& b = *basis;
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
-  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_len_remote.ptr, c_slice_wl.ptr, c_table.ptr, c_slices,
-                      c_code_wide, (u32)(c_table.count / 3)};
+  p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_slice_start.ptr, c_table.ptr, c_slices,
+                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_window, c_rounds, 0u};
   p.phase = phase;
+  p.beside_transfer = beside_transfer ? 1 : 0;
   p.ctx = mp.ctx;
   p.diag_re = mp.diag_re;
   p.diag_im = mp.diag_im;
@@ -463,11 +561,19 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   p.row_hi = std::min<u64>(row_hi, dist.n_local);
   if (p.row_lo >= p.row_hi) return;
   if (p.row_lo & 31) fail(SPED_INTERNAL_ERROR, "row ranges of the cached matvec start at a multiple of 32");
+  u64 const n_entries = dist.chunk * dist.world;  // entries of one replicated column
+  void* scratch = nullptr;
+  if (block > 1) {
+    if (phase != kPhaseAll) fail(SPED_INTERNAL_ERROR, "block applications handle all source classes in one pass");
+    size_t const need_bytes = n_entries * 4 * dtype_size(dtype);
+    if (block_x.count < need_bytes) block_x.alloc(need_bytes);
+    scratch = block_x.ptr;
+  }
   switch (dtype) {
-    case SPED_F32: launch_cached<float>(p, block, xs, ys, s); break;
-    case SPED_F64: launch_cached<double>(p, block, xs, ys, s); break;
-    case SPED_C64: launch_cached<float2>(p, block, xs, ys, s); break;
-    case SPED_C128: launch_cached<double2>(p, block, xs, ys, s); break;
+    case SPED_F32: launch_cached<float>(p, block, xs, ys, n_entries, scratch, s); break;
+    case SPED_F64: launch_cached<double>(p, block, xs, ys, n_entries, scratch, s); break;
+    case SPED_C64: launch_cached<float2>(p, block, xs, ys, n_entries, scratch, s); break;
+    case SPED_C128: launch_cached<double2>(p, block, xs, ys, n_entries, scratch, s); break;
     default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
   }
 }

