@@ -159,13 +159,25 @@ def cpu_sample_rate(O, oop, n, seconds, dtype=np.float64):
     probe = min(n, 512 * O.num_threads())
     stride = max(1, n // probe)
     t0 = time.perf_counter()
-    e = oop.matmat_rows(x, y, 0, n, stride)
+    oop.matmat_rows(x, y, 0, n, stride)
     dt = time.perf_counter() - t0
     rows = len(range(0, n, stride))
     rate_rows = rows / max(dt, 1e-9)
     target = int(max(rows, min(n, rate_rows * seconds)))
     stride = max(1, n // target)
     return x, y, stride
+
+
+def oracle_threads(O):
+    """All host cores for the CPU arm: under torch.distributed.run every rank inherits
+    OMP_NUM_THREADS=1, which would make the CPU baseline a one-core number."""
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    O.set_num_threads(max(1, cores))
+    return O.num_threads()
 
 
 def run_reference(args):
@@ -178,18 +190,11 @@ def run_reference(args):
     from spin_ed_b200 import decks
 
     O.build()
+    cores = oracle_threads(O)
     cfg = decks.load(args.config)
     ob, terms = oracle_problem(O, cfg)
-    cache = os.path.join("/tmp", f"sped_oracle_reps_{args.config}.npy")
     t0 = time.perf_counter()
-    if os.path.exists(cache):
-        ob.build(np.load(cache))
-    else:
-        ob.build()
-        try:
-            np.save(cache, ob.states)
-        except Exception:
-            pass
+    ob.build()  # the CPU arm enumerates its own representatives (no cache, nothing adopted from the GPU)
     build_s = time.perf_counter() - t0
     oop = O.Operator(ob, terms)
     n = ob.number_states
@@ -206,14 +211,14 @@ def run_reference(args):
             elems = rows + e
     t = sum(times) / len(times)
     value = elems / t
-    sample = f"{rows} of {n} rows (every {stride}-th), {elems} matrix elements per step, float64, OpenMP"
+    sample = f"{rows} of {n} rows (every {stride}-th), {elems} matrix elements per step, float64, OpenMP on {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.config, "rows": n, "note": "CPU restatement of the reference path (oracle port), not the "
                    "upstream binary: lattice-symmetries/PRIMME are absent and cannot be built offline"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "extra": {"basis_build_s_cpu": build_s},
     }
@@ -221,42 +226,188 @@ def run_reference(args):
     return 0
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """One process per GPU: rank / world, the torch device, barrier and max-over-ranks helpers."""
 
-    from helpers import splitmix_vector
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        from spin_ed_b200 import ffi
+
+        self.torch, self.dist, self.ffi = torch, dist, ffi
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+        torch.cuda.set_device(self.local)
+        ffi.setDevice(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.oracle_cache = {}
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            box = [ffi.commUniqueId() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ffi.commInit(self.world, self.rank, box[0])
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def finalize(self):
+        if self.world > 1:
+            self.ffi.commFinalize()
+            self.dist.destroy_process_group()
+
+
+def device_splitmix(ctx, rd, lo, hi, seed):
+    """x[i] = uniform(-1,1) from splitmix64(seed ^ GLOBAL row) for the local rows lo..hi-1,
+    generated on the device shard by shard so that 40-spin vectors never exist on the host."""
+    torch = ctx.torch
+
+    def s64(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    out = torch.empty(hi - lo, dtype=torch.float64, device=ctx.dev)
+    lb, bmask = int(rd.log2_block), (1 << int(rd.log2_block)) - 1
+    for c0 in range(lo, hi, 1 << 24):
+        c1 = min(hi, c0 + (1 << 24))
+        i = torch.arange(c0, c1, dtype=torch.int64, device=ctx.dev)
+        g = i if ctx.world == 1 else ((((i >> lb) * ctx.world + ctx.rank) << lb) + (i & bmask))
+        z = (g ^ s64(seed)) + s64(0x9E3779B97F4A7C15)
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
+        z = z ^ ((z >> 31) & ((1 << 33) - 1))
+        out[c0 - lo:c1 - lo] = ((z >> 11) & ((1 << 53) - 1)).to(torch.float64) / 9007199254740992.0 * 2.0 - 1.0
+    return out
+
+
+def replicated_to_global_host(ctx, rd, xfull, n):
+    """The replicated [rank][local] device vector as a host array in GLOBAL row order."""
+    torch = ctx.torch
+    out = np.empty(n, dtype=torch.empty(0, dtype=xfull.dtype).numpy().dtype)
+    lb, bmask, world, chunk = int(rd.log2_block), (1 << int(rd.log2_block)) - 1, ctx.world, int(rd.chunk)
+    for g0 in range(0, n, 1 << 24):
+        g1 = min(n, g0 + (1 << 24))
+        if world == 1:
+            out[g0:g1] = xfull[g0:g1].cpu().numpy()
+            continue
+        g = torch.arange(g0, g1, dtype=torch.int64, device=ctx.dev)
+        blk = g >> lb
+        pos = (blk % world) * chunk + ((blk // world) << lb) + (g & bmask)
+        out[g0:g1] = xfull[pos].cpu().numpy()
+    return out
+
+
+def parity_checks(ctx, cfg, basis, rd, n, np_dtype, xfull, ylocal, n_local, independent_basis, sample_rows, log_prefix):
+    """Oracle checks at size, every world size (rank 0 computes, every rank contributes its rows):
+    (1) the representatives against an INDEPENDENT oracle enumeration -- the whole sector when that
+    takes seconds, otherwise windows of candidate ranks spread over the sector; (2) y = H x of the
+    device path against the oracle on a strided sample of rows, x gathered to the host."""
+    from helpers import oracle_problem
+
+    torch, ffi = ctx.torch, ctx.ffi
+    world, rank = ctx.world, ctx.rank
+    stride = max(1, n // max(1, sample_rows))
+    g = np.arange(0, n, stride, dtype=np.int64)
+    lb, bmask = int(rd.log2_block), (1 << int(rd.log2_block)) - 1
+    if world == 1:
+        owner, loc = np.zeros_like(g), g
+    else:
+        blk = g >> lb
+        owner, loc = blk % world, ((blk // world) << lb) + (g & bmask)
+    mine = owner == rank
+    vals = ylocal[torch.from_numpy(loc[mine]).to(ctx.dev)].cpu().numpy() if mine.any() else np.zeros(0, dtype=np_dtype)
+    parts = ctx.gather_objects((np.nonzero(mine)[0], vals))
+    out = {}
+    if rank == 0:
+        from oracle import oracle as O
+
+        O.build()
+        cores = oracle_threads(O)
+        y_gpu = np.zeros(len(g), dtype=np_dtype)
+        for where, v in parts:
+            y_gpu[where] = v
+        reps = np.asarray(ffi.basisGetStates(basis))
+        ob, terms = oracle_problem(O, cfg)
+        t0 = time.perf_counter()
+        if independent_basis == "full":
+            ob.build()
+            equal = bool(np.array_equal(ob.states, reps))
+            out["basis_check"] = {"kind": "independent oracle enumeration of the whole sector", "equal": equal,
+                                  "oracle_build_s": time.perf_counter() - t0, "cores": cores}
+            if not equal:
+                raise SystemExit(f"{log_prefix}: representatives differ from the oracle's independent enumeration")
+        else:
+            total = ob.sector_candidates
+            windows, width, found, bad = 64, 1 << 21, 0, 0
+            for w in range(windows):
+                lo = int((total - width) * w / max(1, windows - 1)) if total > width else 0
+                r, w0, w1 = ob.build_range(lo, min(total, lo + width))
+                i0 = int(np.searchsorted(reps, np.uint64(w0), side="left"))
+                i1 = len(reps) if w1 == 2**64 - 1 else int(np.searchsorted(reps, np.uint64(w1), side="left"))
+                found += len(r)
+                bad += 0 if np.array_equal(reps[i0:i1], r) else 1
+                if total <= width:
+                    break
+            out["basis_check"] = {"kind": f"independent oracle enumeration of {windows} windows of 2^21 candidate ranks "
+                                          "spread over the sector, each compared with the same range of the GPU array",
+                                  "equal": bad == 0, "representatives_compared": found,
+                                  "oracle_build_s": time.perf_counter() - t0, "cores": cores}
+            if bad:
+                raise SystemExit(f"{log_prefix}: representatives differ from the oracle in {bad} sampled windows")
+            ob.adopt_lazy(reps)  # norms derived per use: the eager O(N |G|) pass would take minutes here
+        oop = O.Operator(ob, terms)
+        x_host = replicated_to_global_host(ctx, rd, xfull, n)
+        t0 = time.perf_counter()
+        want, e = oop.matmat_list(x_host, g.astype(np.uint64))
+        dt = time.perf_counter() - t0
+        err = float(np.linalg.norm(want - y_gpu) / max(np.linalg.norm(want), 1e-300))
+        out["sample_parity_rel_l2"] = err
+        out["sample_parity"] = {"rows": int(len(g)), "stride": int(stride), "matrix_elements": int(len(g) + e),
+                                "oracle_seconds": dt, "tolerance": 1e-12}
+        log(f"{log_prefix}: basis check {out['basis_check']['equal']}, sample parity {err:.2e} on {len(g)} rows")
+        if not err <= 1e-12:
+            raise SystemExit(f"{log_prefix}: device matvec differs from the oracle on the row sample: {err:.3e}")
+        del x_host
+        if independent_basis == "full":
+            ctx.oracle_cache[log_prefix] = (ob, terms)  # the CPU-baseline leg times this same (independent) basis
+    ctx.barrier()
+    return out
+
+
+def bench_deck(ctx, name, args, headline):
+    """Everything measured on one deck.  headline: the full set of legs (block applications, f32
+    storage, host-buffer e2e, CPU baseline); otherwise the sharded-size subset."""
+    torch, dist, ffi = ctx.torch, ctx.dist, ctx.ffi
     from spin_ed_b200 import config as sconfig
-    from spin_ed_b200 import decks, ffi
+    from spin_ed_b200 import decks
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
-    torch.cuda.set_device(local)
-    ffi.setDevice(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-        box = [ffi.commUniqueId() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        ffi.commInit(world, rank, box[0])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    cfg = decks.load(args.config)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    cfg = decks.load(name)
     spec = sconfig.parseConfig(cfg)
     uc = sconfig.toConfig(spec)
     basis, op = uc.cBasis, uc.cHamiltonian.operatorObject
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     ffi.buildBasis(basis)
-    barrier()
+    ctx.barrier()
     build_wall = time.perf_counter() - t0
     n = ffi.getNumberStates(basis)
     is_real = ffi.isOperatorReal(op)
@@ -264,36 +415,37 @@ def run_ours(args):
     t_dtype = torch.float64 if is_real else torch.complex128
     tag = ffi.DTYPE_TAGS[np.dtype(np_dtype)]
     es = np.dtype(np_dtype).itemsize
-    rows = n
     rd = ffi.basisRowDistribution(basis)  # block-cyclic rows of this rank, [rank][local] vector layout
     n_local, chunk = int(rd.n_local), int(rd.chunk)
     symmetric = ffi.basisProgramStats(basis)["steps"] > 1 or cfg["basis"].get("spin_inversion") is not None
-    log(f"[rank {rank}] {args.config}: N={n} local rows {n_local} (blocks of {1 << rd.log2_block}) build {build_wall:.3f}s")
+    log(f"[rank {rank}] {name}: N={n} local rows {n_local} (blocks of {1 << rd.log2_block}) build {build_wall:.3f}s")
+    extra = {"basis_build_s": build_wall, "basis_build_device_s": ffi.basisBuildSeconds(basis), "rows": n,
+             "program": ffi.basisProgramStats(basis)}
+
+    def solve(label):
+        ctx.barrier()
+        t0 = time.perf_counter()
+        evals, _, rnorms = ffi.eigh(op, np.dtype(np_dtype), spec.number_vectors, spec.precision, spec.max_primme_basis_size,
+                                    spec.max_primme_block_size, spec.min_primme_restart_size, want_vectors=False)
+        ctx.barrier()
+        dt = time.perf_counter() - t0
+        st = ffi.eighLastStats(op)
+        log(f"[rank {rank}] {name}: {label} eigh {dt:.3f}s E0={evals[0]:.12f} rnorm={rnorms[0]:.2e} matvecs={st['matvecs']}")
+        return dt, [float(v) for v in evals], [float(v) for v in rnorms], st
+
+    # (0) COLD time-to-ground-state: first use of this operator in the process -- includes the NVRTC
+    #     specialisation of the canonicalisation (unless its cubin is in the disk cache), the
+    #     matrix-free traversal that fills the operator cache, and the solve
+    if not args.no_eigh:
+        dt, evals, rnorms, st = solve("cold")
+        extra.update({"time_to_ground_state_cold_s": dt, "eigenvalues": evals, "residual_norms": rnorms,
+                      "cold_includes": "NVRTC compile of the specialised kernels + operator-cache fill + solve"})
+        torch.cuda.empty_cache()
 
     # device-resident inputs: the replicated vector (padded to world * chunk) and the local output
-    # x[i] = uniform(-1,1) from splitmix64(seed ^ global row), generated on the device
-    # shard by shard so that 40-spin vectors never exist on the host
-    def device_splitmix(lo, hi, seed):
-        """values of the local rows lo..hi-1 (local indices), keyed by their GLOBAL row"""
-        def s64(v):
-            return v - (1 << 64) if v >= (1 << 63) else v
-
-        out = torch.empty(hi - lo, dtype=torch.float64, device=dev)
-        lb, bmask = int(rd.log2_block), (1 << int(rd.log2_block)) - 1
-        for c0 in range(lo, hi, 1 << 24):
-            c1 = min(hi, c0 + (1 << 24))
-            i = torch.arange(c0, c1, dtype=torch.int64, device=dev)
-            g = i if world == 1 else ((((i >> lb) * world + rank) << lb) + (i & bmask))
-            z = (g ^ s64(seed)) + s64(0x9E3779B97F4A7C15)
-            z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
-            z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
-            z = z ^ ((z >> 31) & ((1 << 33) - 1))
-            out[c0 - lo:c1 - lo] = ((z >> 11) & ((1 << 53) - 1)).to(torch.float64) / 9007199254740992.0 * 2.0 - 1.0
-        return out
-
     xshard = torch.zeros(chunk, dtype=t_dtype, device=dev)
     if n_local:
-        xshard[:n_local] = device_splitmix(0, n_local, 0x5EED0001).to(t_dtype)
+        xshard[:n_local] = device_splitmix(ctx, rd, 0, n_local, 0x5EED0001).to(t_dtype)
     nrm2 = (xshard.abs() ** 2).sum().to(torch.float64).reshape(1)
     if world > 1:
         dist.all_reduce(nrm2)
@@ -304,112 +456,214 @@ def run_ours(args):
     else:
         xfull.copy_(xshard)
     if n <= 4096 and world == 1:  # the generator must reproduce the host definition used by the tests
+        from helpers import splitmix_vector
+
         ref = splitmix_vector(n, 0x5EED0001, np.float64)
         assert np.allclose(xfull[:n].cpu().numpy().real * float(nrm2.sqrt().item()), ref, rtol=0, atol=1e-15)
     ylocal = torch.zeros(max(n_local, 1), dtype=t_dtype, device=dev)
     stream = torch.cuda.current_stream()
 
     def step():
-        if world > 1:  # what sped_eigh does per matvec: all-gather of the shards overlapped with the local-source pass
+        if world > 1:  # what sped_eigh does per matvec: exchange of the shards overlapped with the passes over the source classes
             ffi.operatorMatvecSharded(op, tag, xshard.data_ptr(), ylocal.data_ptr(), xfull.data_ptr(), stream.cuda_stream)
         else:
             ffi.operatorMatmatDevice(op, tag, 1, xfull.data_ptr(), chunk * world, ylocal.data_ptr(), max(n_local, 1),
                                      stream.cuda_stream)
 
+    def kernel_only(t, x, y, cols=1):
+        ffi.operatorMatmatDevice(op, t, cols, x.data_ptr(), chunk * world, y.data_ptr(), max(n_local, 1), stream.cuda_stream)
+
+    def timed(fn, reps):
+        ctx.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        ctx.barrier()
+        return a.elapsed_time(b) / reps
+
     # (a) matrix-free kernel alone (what the first application of an operator costs, and the only
     #     mode when the element cache does not fit): a few steps, device events
     ffi.operatorSetCache(op, 0)
     step()
-    barrier()
-    mf_steps = max(2, min(args.steps, 3))
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(mf_steps):
-        step()
-    b.record()
-    barrier()
-    mf_t = torch.tensor([a.elapsed_time(b) / mf_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(mf_t, op=dist.ReduceOp.MAX)
-    matrix_free_ms = float(mf_t.item())
+    ctx.barrier()
+    matrix_free_ms = ctx.allmax(timed(step, max(2, min(args.steps, 3))))
     # (b) the default path: elements cached in HBM by the first application (if they fit)
     ffi.operatorSetCache(op, -1)
     for _ in range(args.warmup):
         step()
-    barrier()
+    ctx.barrier()
     cache_info = ffi.operatorCacheInfo(op)
     rows, n_off = ffi.operatorCountElements(op)  # E: off-diagonal elements one application touches
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
     launches0 = ffi.kernelLaunches()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
+    ctx.barrier()
     ev[0].record()
     for i in range(args.steps):
         step()
         ev[i + 1].record()
-    barrier()
+    ctx.barrier()
     launches = ffi.kernelLaunches() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    t_local = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    total_ms = float(t_local.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = ctx.allmax(ev[0].elapsed_time(ev[-1])) / args.steps
     value = (rows + n_off) / (ms_per_step * 1e-3)
-    # dominant kernel: the matvec kernel is the only kernel of ours in a step
-    kern_ms = ms_per_step if world == 1 else None
-    if world > 1:
-        # time the kernel alone (no all-gather) for the per-GPU roofline
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            ffi.operatorMatmatDevice(op, tag, 1, xfull.data_ptr(), chunk * world, ylocal.data_ptr(), max(n_local, 1),
-                                     stream.cuda_stream)
-        b.record()
-        barrier()
-        kern_ms = a.elapsed_time(b) / args.steps
-    kern_all = [kern_ms]
-    if world > 1:
-        kern_all = [None] * world
-        dist.all_gather_object(kern_all, kern_ms)
-        kern_ms = max(kern_all)  # the slowest rank bounds the step
+    # dominant kernel alone: at one GPU it is the step; at several the exchange is left out
+    kern_ms = ms_per_step if world == 1 else timed(lambda: kernel_only(tag, xfull, ylocal), args.steps)
+    kern_all = ctx.gather_objects(kern_ms)
+    kern_ms = max(kern_all)  # the slowest rank bounds the step
+    step()  # leave y = H x of the sharded step in ylocal (the kernel-only leg wrote the same values)
+    ctx.barrier()
     peak, peak_src = measured_peak()
     local_off = n_off * n_local / max(n, 1)
     alg_bytes = algorithmic_bytes(n_local, local_off, es, symmetric)
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    extra.update({"offdiag_elements": n_off, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_per_rank": kern_all,
+                  "operator_cache": cache_info, "cached_variant": os.environ.get("SPED_CACHED_VARIANT", "default"),
+                  "matrix_free": {"ms_per_step": matrix_free_ms, "value": (rows + n_off) / (matrix_free_ms * 1e-3),
+                                  "unit": UNIT, "roofline_frac_hbm": alg_bytes / (matrix_free_ms * 1e-3) / 1e9 / peak,
+                                  "note": "integer-ALU bound: canonicalisation over the symmetry group per element"}})
 
-    # the same kernel with single-precision storage (what `datatype: float32` decks such as 6x6 ask
-    # for; accumulation stays f64): kernel only, reported beside the f64 headline
-    f32_leg = None
-    if is_real:
+    # oracle checks at size (every world size): independent representatives + row-sample parity
+    if not args.no_parity:
+        full = n <= 64_000_000 and headline
+        extra.update(parity_checks(ctx, cfg, basis, rd, n, np_dtype, xfull, ylocal, n_local, "full" if full else "windows",
+                                   args.parity_rows, f"{name} x{world}"))
+
+    f32_leg = block_leg = None
+    if headline and is_real:
+        # the same kernel with single-precision storage (what `datatype: float32` decks such as 6x6
+        # ask for; accumulation stays f64): kernel only, reported beside the f64 headline
         x32 = xfull.to(torch.float32)
         y32 = torch.zeros(max(n_local, 1), dtype=torch.float32, device=dev)
         tag32 = ffi.DTYPE_TAGS[np.dtype(np.float32)]
         for _ in range(3):
-            ffi.operatorMatmatDevice(op, tag32, 1, x32.data_ptr(), chunk * world, y32.data_ptr(), max(n_local, 1),
-                                     stream.cuda_stream)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            ffi.operatorMatmatDevice(op, tag32, 1, x32.data_ptr(), chunk * world, y32.data_ptr(), max(n_local, 1),
-                                     stream.cuda_stream)
-        b.record()
-        barrier()
-        t32 = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t32, op=dist.ReduceOp.MAX)
-        ms32 = float(t32.item())
+            kernel_only(tag32, x32, y32)
+        ms32 = ctx.allmax(timed(lambda: kernel_only(tag32, x32, y32), args.steps))
         bytes32 = algorithmic_bytes(n_local, local_off, 4, symmetric)
         f32_leg = {"kernel_ms": ms32, "value": (rows + n_off) / (ms32 * 1e-3) if world == 1 else None, "unit": UNIT,
                    "algorithmic_bytes_per_launch": bytes32, "roofline_frac_hbm": bytes32 / (ms32 * 1e-3) / 1e9 / peak,
                    "rel_l2_vs_f64": float(((y32[:n_local].double() - ylocal[:n_local]).norm() /
                                            ylocal[:n_local].norm().clamp_min(1e-300)).item()) if n_local else 0.0}
         del x32, y32
+    if headline and world == 1:
+        # block applications (what the solver issues with max_primme_block_size > 1): 2 and 4 columns
+        xb = torch.stack([torch.roll(xfull, -c) for c in range(4)]).contiguous()
+        yb = torch.zeros(4, max(n_local, 1), dtype=t_dtype, device=dev)
+        block_leg = {}
+        for cols in (2, 4):
+            for _ in range(2):
+                kernel_only(tag, xb, yb, cols)
+            ms = timed(lambda: kernel_only(tag, xb, yb, cols), max(3, args.steps // 3))
+            block_leg[f"columns_{cols}"] = {"ms": ms, "value": cols * (rows + n_off) / (ms * 1e-3), "unit": UNIT,
+                                            "col0_max_abs_diff_vs_single": float((yb[0, :n_local] - ylocal[:n_local]).abs().max().item())}
+        del xb, yb
+    extra["float32_storage"] = f32_leg
+    extra["block_applications"] = block_leg
+
+    # end-to-end through the reference-facing C ABI with host buffers
+    e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": n * es, "d2h_bytes_per_step": n * es}
+    if not headline:
+        e2e["skipped"] = "host-buffer leg runs on the headline deck only"
+    elif 2 * n * es * world > args.e2e_host_gb * 1e9:
+        e2e["skipped"] = f"pinned host buffers would need {2 * n * es * world / 1e9:.0f} GB on this node (--e2e-host-gb)"
+    else:
+        y_host = torch.zeros(n, dtype=t_dtype).pin_memory().numpy()
+        x_host_t = torch.empty(n, dtype=t_dtype).pin_memory()
+        x_host_t.copy_(torch.from_numpy(replicated_to_global_host(ctx, rd, xfull, n)))
+        x_host = x_host_t.numpy()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            ffi.inplaceApply(op, x_host, y_host)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ffi.inplaceApply(op, x_host, y_host)
+        ctx.barrier()
+        e2e_t = ctx.allmax((time.perf_counter() - t0) / e2e_steps)
+        e2e["value"] = (rows + n_off) / e2e_t
+        e2e["ms_per_call"] = e2e_t * 1e3
+        # consistency of the two paths (same rows, same data)
+        dev_y = ylocal[:n_local].cpu().numpy()
+        host_rows = y_host[rd.local_rows().astype(np.int64)] if n_local else dev_y
+        dev_err = float(np.abs(dev_y - host_rows).max() / max(np.abs(dev_y).max(), 1e-300)) if n_local else 0.0
+        e2e["max_rel_diff_vs_device_path"] = dev_err
+        if dev_err > 1e-13:
+            raise SystemExit(f"device-resident and host-pointer matvec disagree: {dev_err:.3e}")
+        del y_host, x_host_t, x_host
+
+    # CPU baseline (rank 0, one GPU only): the oracle port on the host cores, bounded row sample
+    cpu_baseline = None
+    if headline and rank == 0 and world == 1 and not args.no_cpu:
+        from helpers import oracle_problem
+        from oracle import oracle as O
+
+        O.build()
+        cores = oracle_threads(O)
+        if f"{name} x{world}" in ctx.oracle_cache:  # the oracle's own enumeration (parity_checks compared it with the GPU's)
+            ob, terms = ctx.oracle_cache.pop(f"{name} x{world}")
+        else:
+            ob, terms = oracle_problem(O, cfg)
+            ob.build()
+            if not np.array_equal(ob.states, np.asarray(ffi.basisGetStates(basis))):
+                raise SystemExit(f"{name}: representatives differ from the oracle's independent enumeration")
+        oop = O.Operator(ob, terms)
+        xs, ys, stride = cpu_sample_rate(O, oop, n, args.cpu_seconds, np_dtype)
+        t0 = time.perf_counter()
+        e = oop.matmat_rows(xs, ys, 0, n, stride)
+        dt = time.perf_counter() - t0
+        srows = len(range(0, n, stride))
+        cpu_baseline = {"value": (srows + e) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{srows} of {n} rows (every {stride}-th), {srows + e} matrix elements, {dt:.1f} s; "
+                                  "oracle port (OpenMP), not the upstream binary"}
+        del ob, oop, xs, ys
+
+    # WARM time-to-ground-state: kernels already specialised; still includes the cache fill
+    if not args.no_eigh:
+        ffi.operatorSetCache(op, -1)  # drop the cache: time-to-ground-state includes building it
+        del xfull, xshard, ylocal      # the solver allocates its own vectors (42 spins: 25.6 GB each)
+        torch.cuda.empty_cache()
+        dt, evals, rnorms, st = solve("warm")
+        for a, b in zip(evals, extra["eigenvalues"]):
+            if abs(a - b) > 1e-9 * max(1.0, abs(a)):
+                raise SystemExit(f"{name}: cold and warm solves disagree: {extra['eigenvalues']} vs {evals}")
+        extra.update({"time_to_ground_state_s": dt, "eigenvalues": evals, "residual_norms": rnorms, "eigh_matvecs": st["matvecs"],
+                      "eigh_restarts": st["restarts"], "eigh_seconds_matvec": st["seconds_matvec"], "eigh_stats": st,
+                      "eigh_dtype": "f64 (deck asks " + spec.datatype + ")"})
+    ffi.operatorSetCache(op, -1)
+    torch.cuda.empty_cache()
+    return {"name": name, "rows": rows, "n_off": n_off, "ms_per_step": ms_per_step, "value": value, "kern_ms": kern_ms,
+            "alg_bytes": alg_bytes, "achieved": achieved, "peak": peak, "clocks": clocks, "launches": int(launches),
+            "e2e": e2e, "cpu_baseline": cpu_baseline, "extra": extra, "is_real": is_real, "cache_ready": cache_info["ready"]}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    world, rank = ctx.world, ctx.rank
+    r = bench_deck(ctx, args.config, args, headline=True)
+    extra = r["extra"]
+    # the sharded north-star deck beside the headline one whenever there is more than one GPU
+    # (BASELINE.json: heisenberg_chain_40 over 2/4/8 B200); step-time roofline fraction included
+    sharded = {}
+    if world > 1 and args.sharded_deck and args.sharded_deck != args.config:
+        s = bench_deck(ctx, args.sharded_deck, args, headline=False)
+        sx = s["extra"]
+        sharded = {
+            "workload": s["name"], "rows": s["rows"], "offdiag_elements": s["n_off"], "ms_per_step": s["ms_per_step"],
+            "value": s["value"], "unit": UNIT, "kernel_ms": s["kern_ms"],
+            "roofline_frac_kernel": s["achieved"] / s["peak"],
+            "roofline_frac_on_step": s["alg_bytes"] / (s["ms_per_step"] * 1e-3) / 1e9 / s["peak"],
+            "E0": (sx.get("eigenvalues") or [None])[0], "rnorm": (sx.get("residual_norms") or [None])[0],
+            "matvecs": sx.get("eigh_matvecs"), "time_to_ground_state_s": sx.get("time_to_ground_state_s"),
+            "time_to_ground_state_cold_s": sx.get("time_to_ground_state_cold_s"),
+            "sample_parity_rel_l2": sx.get("sample_parity_rel_l2"), "basis_check": sx.get("basis_check"),
+            "basis_build_s": sx["basis_build_s"], "matrix_free_ms": sx["matrix_free"]["ms_per_step"],
+            "operator_cache": sx["operator_cache"], "eigh_stats": sx.get("eigh_stats"), "kernel_ms_per_rank": sx["kernel_ms_per_rank"],
+        }
+        extra[s["name"].replace("heisenberg_", "")] = sharded
     traffic = None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (one-GPU runs only)
         if world > 1:
@@ -418,108 +672,28 @@ def run_ours(args):
             traffic = json.load(f).get(args.config, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-
-    # end-to-end through the reference-facing C ABI with host buffers
-    e2e = None
-    y_host = None
-    if 2 * n * es * world <= args.e2e_host_gb * 1e9:
-        y_host = torch.zeros(n, dtype=t_dtype).pin_memory().numpy()
-        x_host_t = torch.empty(n, dtype=t_dtype).pin_memory()
-        if world == 1:
-            x_host_t.copy_(xfull[:n])
-        else:  # back to global row order for the host-pointer call
-            pos = torch.from_numpy(rd.global_to_position(np.arange(n, dtype=np.uint64)).astype(np.int64)).to(dev)
-            x_host_t.copy_(xfull[pos])
-            del pos
-        x_host = x_host_t.numpy()
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            ffi.inplaceApply(op, x_host, y_host)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            ffi.inplaceApply(op, x_host, y_host)
-        barrier()
-        e2e_t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e = {"value": (rows + n_off) / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": n * es,
-               "d2h_bytes_per_step": n * es}
-        # consistency of the two paths (same rows, same data)
-        dev_y = ylocal[:n_local].cpu().numpy()
-        if n_local and not np.array_equal(dev_y, y_host[rd.local_rows().astype(np.int64)]):
-            raise SystemExit("device-resident and host-pointer matvec disagree")
-    else:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": n * es, "d2h_bytes_per_step": n * es,
-               "skipped": f"pinned host buffers would need {2 * n * es * world / 1e9:.0f} GB on this node (--e2e-host-gb)"}
-
-    mf_achieved = alg_bytes / (matrix_free_ms * 1e-3) / 1e9
-    extra = {"basis_build_s": build_wall, "basis_build_device_s": ffi.basisBuildSeconds(basis), "rows": rows,
-             "offdiag_elements": n_off, "program": ffi.basisProgramStats(basis), "peak_source": peak_src,
-             "kernel_ms": kern_ms, "kernel_ms_per_rank": kern_all, "operator_cache": cache_info,
-             "float32_storage": f32_leg, "cached_variant": os.environ.get("SPED_CACHED_VARIANT", "default"),
-             "matrix_free": {"ms_per_step": matrix_free_ms, "value": (rows + n_off) / (matrix_free_ms * 1e-3),
-                             "unit": UNIT, "roofline_frac_hbm": mf_achieved / peak,
-                             "note": "integer-ALU bound: canonicalisation over the symmetry group per element"}}
-    if not args.no_eigh:
-        ffi.operatorSetCache(op, -1)  # drop the cache: time-to-ground-state includes building it
-        del xfull, xshard, ylocal      # the solver allocates its own vectors (42 spins: 25.6 GB each)
-        torch.cuda.empty_cache()
-        barrier()
-        t0 = time.perf_counter()
-        evals, _, rnorms = ffi.eigh(op, np.dtype(np_dtype), spec.number_vectors, spec.precision, spec.max_primme_basis_size,
-                                    spec.max_primme_block_size, spec.min_primme_restart_size, want_vectors=False)
-        barrier()
-        st = ffi.eighLastStats(op)
-        extra.update({"time_to_ground_state_s": time.perf_counter() - t0, "eigenvalues": [float(v) for v in evals],
-                      "residual_norms": [float(v) for v in rnorms], "eigh_matvecs": st["matvecs"],
-                      "eigh_restarts": st["restarts"], "eigh_seconds_matvec": st["seconds_matvec"], "eigh_stats": st,
-                      "eigh_dtype": "f64 (deck asks " + spec.datatype + ")"})
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu and y_host is not None:
-        from helpers import oracle_problem
-        from oracle import oracle as O
-
-        O.build()
-        ob, terms = oracle_problem(O, cfg)
-        ob.build(np.array(ffi.basisGetStates(basis)))  # adopt the representatives (oracle computes its own norms)
-        oop = O.Operator(ob, terms)
-        xs, ys, stride = cpu_sample_rate(O, oop, n, args.cpu_seconds, np_dtype)
-        t0 = time.perf_counter()
-        e = oop.matmat_rows(xs, ys, 0, n, stride)
-        dt = time.perf_counter() - t0
-        srows = len(range(0, n, stride))
-        # the sampled rows must agree with the GPU result (full-size parity on the sample)
-        gpu_rows = y_host[0:n:stride]
-        err = np.linalg.norm(ys[0:n:stride] - gpu_rows) / max(np.linalg.norm(gpu_rows), 1e-300)
-        extra["sample_parity_rel_l2"] = float(err)
-        cpu_baseline = {"value": (srows + e) / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
-                        "sample": f"{srows} of {n} rows (every {stride}-th), {srows + e} matrix elements, {dt:.1f} s; "
-                                  "oracle port (OpenMP), not the upstream binary"}
-
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if is_real else "c128", "data": "synthetic",
-            "config": {"workload": args.config, "rows": rows, "offdiag_elements": n_off, "block_size": 1,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if r["is_real"] else "c128", "data": "synthetic",
+            "config": {"workload": args.config, "rows": r["rows"], "offdiag_elements": r["n_off"], "block_size": 1,
                        "path": ("operator elements cached in HBM by the first (matrix-free) application; steady-state "
-                                "matvec streams them" if cache_info["ready"] else "matrix-free every application"),
-                       "parallelism": f"rows dealt block-cyclically over {world} GPU(s); per matvec one NCCL all-gather of the "
-                                      "Krylov vector, overlapped with the local-source part of the product",
-                       "l2": "inputs larger than L2 (no flush)" if alg_bytes > 126e6 else "inputs fit in L2 (no flush)"},
-            "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes},
-            "cpu_baseline": cpu_baseline, "extra": extra,
+                                "matvec streams them" if r["cache_ready"] else "matrix-free every application"),
+                       "parallelism": f"rows dealt block-cyclically over {world} GPU(s); per matvec the Krylov vector is exchanged "
+                                      "over NVLink (NCCL), overlapped with the passes over the source classes of the product",
+                       "l2": "inputs larger than L2 (no flush)" if r["alg_bytes"] > 126e6 else "inputs fit in L2 (no flush)"},
+            "clocks": r["clocks"],
+            "e2e": r["e2e"],
+            "gpu_launches": r["launches"],
+            "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s",
+                         "frac": r["achieved"] / r["peak"], "traffic": traffic,
+                         "algorithmic_bytes_per_launch": r["alg_bytes"],
+                         "frac_on_step": r["alg_bytes"] / (r["ms_per_step"] * 1e-3) / 1e9 / r["peak"]},
+            "cpu_baseline": r["cpu_baseline"], "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        ffi.commFinalize()
-        dist.destroy_process_group()
+    ctx.finalize()
     return 0
 
 
@@ -530,12 +704,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_DECK)
+    ap.add_argument("--sharded-deck", default="heisenberg_chain_40",
+                    help="with more than one GPU this deck is measured as well (extra.<deck>); '' to skip")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--parity-rows", type=int, default=100_000, help="rows of the oracle parity sample")
     ap.add_argument("--e2e-host-gb", type=float, default=24.0, help="skip the host-buffer leg above this much pinned memory")
     ap.add_argument("--watchdog-seconds", type=float, default=1500.0,
                     help="abort the process if the whole run takes longer (a mismatched collective hangs every rank)")
     ap.add_argument("--no-eigh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.watchdog_seconds > 0:

@@ -22,18 +22,6 @@ int sped_selftest_jit_source(void const* basis, char* out, uint64_t capacity, ui
 /* Compiles the specialised matvec kernel with NVRTC for sm_100a without loading it (no GPU
  * needed); returns the cubin size. */
 int sped_selftest_jit_compile(void const* basis, int dtype, int columns, uint64_t* cubin_bytes);
-/* Single-threaded HOST emulation of the matvec kernels (csrc/emul.cpp: the device sources compiled
- * by the host compiler with the CUDA built-ins shimmed) on a small problem whose representatives
- * and stabiliser sizes the caller supplies (the test-suite takes them from the oracle): y = H x for
- * the rows rank `rank` of `world` owns, computed by the matrix-free row routine (y_free), by the
- * streaming kernel over all source classes at once (y_all) and class by class (y_phased).
- * dtype: 1 = f64, 3 = c128; x in global row order.  stats[5] = slots, stored elements, elements
- * with the default coefficient, source classes, elements of the window class.  With ncols = 2..4 the block kernel is run as well
- * on the columns x_c[g] = x[(g + c) mod n] (y_block: n_local x ncols, column-major).
- * Verification only: nothing in the product calls it. */
-int sped_selftest_emulate_matvec(void const* op, uint64_t n, uint64_t const* reps, uint16_t const* stab, int world, int rank,
-                                 int dtype, void const* x_global, void* y_free, void* y_all, void* y_phased,
-                                 uint64_t* stats, unsigned ncols, void* y_block);
 #ifdef __cplusplus
 }
 #endif

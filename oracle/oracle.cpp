@@ -277,6 +277,7 @@ struct Basis {
   bool use_naive = false;  // test hook: bit-by-bit permutations instead of Benes
   std::vector<u64> reps;
   std::vector<double> norms;
+  bool lazy_norms = false;  // adopted without the O(N |G|) norm pass (bounded samples of huge sectors)
   // lookup: prefix buckets on the top `pbits` bits of the n-bit word
   int pbits = 0, pshift = 0;
   std::vector<u64> bucket;
@@ -333,6 +334,15 @@ struct Basis {
   }
 
   double norm_from_stab(int stab) const { return std::sqrt((double)stab / (double)gsize()); }
+
+  // norm of representative number idx (computed on demand when the basis was adopted lazily)
+  double norm_at(u64 idx) const {
+    if (!lazy_norms) return norms[idx];
+    if (trivial()) return 1.0;
+    u64 rep; cplx chi; int stab;
+    state_info(reps[idx], rep, chi, stab);
+    return norm_from_stab(stab);
+  }
 
   // is x an orbit minimum with non-zero norm?  (early exit on the first smaller image)
   bool is_representative(u64 x, int& stab_out) const {
@@ -418,6 +428,7 @@ inline u64 next_same_popcount(u64 x) {
 }
 
 int build_basis(Basis& b) {
+  b.lazy_norms = false;
   b.reps.clear();
   b.norms.clear();
   const int n = b.n;
@@ -488,21 +499,28 @@ template <> struct Scalar<std::complex<float>> { static cplx load(const std::com
 template <> struct Scalar<cplx> { static cplx load(const cplx* p) { return *p; } static void store(cplx* p, cplx v) { *p = v; } };
 
 // y = H x (column-major blocks), optionally also counts matrix elements
+// rows row_lo, row_lo + stride, ... < row_hi; or, with row_list != null, exactly the n_list listed rows,
+// whose results are then stored compactly (y[c * ys + k] for the k-th listed row)
 template <class T>
 int matmat(const Operator& op, u64 size, u64 block, const T* x, u64 xs, T* y, u64 ys, u64* n_offdiag,
-           u64 row_lo = 0, u64 row_hi = ~0ull, u64 row_stride = 1) {
+           u64 row_lo = 0, u64 row_hi = ~0ull, u64 row_stride = 1, const u64* row_list = nullptr, u64 n_list = 0) {
   const Basis& B = *op.basis;
   if (!B.built) return ORC_NOT_BUILT;
   if (size != B.reps.size()) return ORC_DIMENSION_MISMATCH;
   u64 count = 0;
   if (row_hi > size) row_hi = size;
   if (row_stride == 0) row_stride = 1;
-  const i64 n_rows = row_hi > row_lo ? (i64)((row_hi - row_lo + row_stride - 1) / row_stride) : 0;
+  i64 n_rows = row_hi > row_lo ? (i64)((row_hi - row_lo + row_stride - 1) / row_stride) : 0;
+  if (row_list) {
+    n_rows = (i64)n_list;
+    for (u64 k = 0; k < n_list; ++k)
+      if (row_list[k] >= size) return ORC_INVALID_ARGUMENT;
+  }
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : count)
   for (i64 it = 0; it < n_rows; ++it) {
-    const i64 row = (i64)(row_lo + (u64)it * row_stride);
+    const i64 row = row_list ? (i64)row_list[it] : (i64)(row_lo + (u64)it * row_stride);
     const u64 r = B.reps[row];
-    const double nr = B.norms[row];
+    const double nr = B.norm_at(row);
     std::vector<cplx> acc(block, cplx(0, 0));
     for (auto const& t : op.terms) {
       const int k = t.k, dim = 1 << k;
@@ -531,13 +549,13 @@ int matmat(const Operator& op, u64 size, u64 block, const T* x, u64 xs, T* y, u6
           i64 idx = B.index_of(rep);
           if (idx < 0) continue;
           ++count;
-          cplx w = h * chi * (B.norms[idx] / nr);
+          cplx w = h * chi * (B.norm_at(idx) / nr);
           for (u64 c = 0; c < block; ++c) acc[c] += w * Scalar<T>::load(x + c * xs + idx);
         }
       }
     }
     if (y)
-      for (u64 c = 0; c < block; ++c) Scalar<T>::store(y + c * ys + row, acc[c]);
+      for (u64 c = 0; c < block; ++c) Scalar<T>::store(y + c * ys + (row_list ? it : row), acc[c]);
   }
   if (n_offdiag) *n_offdiag = count;
   return ORC_OK;
@@ -575,6 +593,7 @@ int orc_periodicity(int n, const int* perm) {
 int orc_basis_build(void* b) { return build_basis(*(Basis*)b); }
 int orc_basis_build_unsafe(void* bp, u64 size, const u64* reps) {
   Basis& b = *(Basis*)bp;
+  b.lazy_norms = false;
   b.reps.assign(reps, reps + size);
   b.norms.resize(size);
 #pragma omp parallel for
@@ -586,6 +605,60 @@ int orc_basis_build_unsafe(void* bp, u64 size, const u64* reps) {
   b.build_index();
   b.built = true;
   return ORC_OK;
+}
+// adopt without computing the norms (they are derived per use): for bounded samples of sectors
+// with ~10^9 representatives, where the eager pass alone would take minutes of CPU time
+int orc_basis_adopt_lazy(void* bp, u64 size, const u64* reps) {
+  Basis& b = *(Basis*)bp;
+  b.reps.assign(reps, reps + size);
+  b.norms.clear();
+  b.lazy_norms = true;
+  b.build_index();
+  b.built = true;
+  return ORC_OK;
+}
+// representatives among the candidates of combinatorial rank [rank_lo, rank_hi) of the sector
+// (independent enumeration of a window of a huge sector); returns their number, writes at most cap
+// of them to out, and the first / one-past-last candidate WORD of the window to word_range[2]
+// (word_range[1] = ~0 when the window reaches the end of the sector).
+u64 orc_basis_build_range(void* bp, u64 rank_lo, u64 rank_hi, u64 cap, u64* out, u64* word_range) {
+  Basis& b = *(Basis*)bp;
+  const int n = b.n;
+  u64 total = b.hw >= 0 ? binom(n, b.hw) : (n == 64 ? ~0ull : (1ull << n));
+  rank_hi = std::min(rank_hi, total);
+  if (rank_lo >= rank_hi) { word_range[0] = word_range[1] = ~0ull; return 0; }
+  auto word = [&](u64 r) { return b.hw >= 0 ? (b.hw == 0 ? 0ull : unrank(r, b.hw)) : r; };
+  word_range[0] = word(rank_lo);
+  word_range[1] = rank_hi < total ? word(rank_hi) : ~0ull;
+  int nthreads = 1;
+#ifdef _OPENMP
+  nthreads = omp_get_max_threads();
+#endif
+  const u64 span = rank_hi - rank_lo;
+  size_t nchunks = std::max<size_t>(1, std::min<u64>(span / 4096 + 1, (u64)nthreads * 16));
+  std::vector<std::vector<u64>> found(nchunks);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (size_t c = 0; c < nchunks; ++c) {
+    u64 lo = rank_lo + (u64)((__uint128_t)span * c / nchunks), hi = rank_lo + (u64)((__uint128_t)span * (c + 1) / nchunks);
+    if (lo >= hi) continue;
+    u64 x = word(lo);
+    for (u64 r = lo; r < hi; ++r) {
+      int stab = 1;
+      if (b.trivial() || b.is_representative(x, stab)) found[c].push_back(x);
+      if (r + 1 < hi) x = b.hw >= 0 ? next_same_popcount(x) : x + 1;
+    }
+  }
+  u64 count = 0;
+  for (auto const& v : found)
+    for (u64 x : v) {
+      if (count < cap) out[count] = x;
+      ++count;
+    }
+  return count;
+}
+u64 orc_sector_candidates(void* bp) {
+  Basis& b = *(Basis*)bp;
+  return b.hw >= 0 ? binom(b.n, b.hw) : (b.n == 64 ? ~0ull : (1ull << b.n));
 }
 u64 orc_basis_size(void* b) { return ((Basis*)b)->reps.size(); }
 void orc_basis_states(void* b, u64* out) { auto& r = ((Basis*)b)->reps; std::memcpy(out, r.data(), r.size() * 8); }
@@ -632,6 +705,19 @@ int orc_operator_matmat_rows(void* op, int dtype, u64 size, u64 block, const voi
     case 1: return matmat<double>(o, size, block, (const double*)x, xs, (double*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
     case 2: return matmat<std::complex<float>>(o, size, block, (const std::complex<float>*)x, xs, (std::complex<float>*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
     case 3: return matmat<cplx>(o, size, block, (const cplx*)x, xs, (cplx*)y, ys, n_offdiag, row_lo, row_hi, row_stride);
+  }
+  return ORC_INVALID_DATATYPE;
+}
+// exactly the listed rows; y_out[k] = (H x)[rows[k]] (one column, compact)
+int orc_operator_matmat_list(void* op, int dtype, u64 size, const void* x, u64 n_rows, const u64* rows, void* y_out,
+                             u64* n_offdiag) {
+  Operator& o = *(Operator*)op;
+  if ((dtype == 0 || dtype == 1) && !o.is_real()) return ORC_INVALID_DATATYPE;
+  switch (dtype) {
+    case 0: return matmat<float>(o, size, 1, (const float*)x, size, (float*)y_out, n_rows, n_offdiag, 0, ~0ull, 1, rows, n_rows);
+    case 1: return matmat<double>(o, size, 1, (const double*)x, size, (double*)y_out, n_rows, n_offdiag, 0, ~0ull, 1, rows, n_rows);
+    case 2: return matmat<std::complex<float>>(o, size, 1, (const std::complex<float>*)x, size, (std::complex<float>*)y_out, n_rows, n_offdiag, 0, ~0ull, 1, rows, n_rows);
+    case 3: return matmat<cplx>(o, size, 1, (const cplx*)x, size, (cplx*)y_out, n_rows, n_offdiag, 0, ~0ull, 1, rows, n_rows);
   }
   return ORC_INVALID_DATATYPE;
 }

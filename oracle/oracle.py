@@ -56,6 +56,12 @@ def lib():
         L.orc_periodicity.argtypes = [ci, vp]
         L.orc_basis_build.argtypes = [vp]
         L.orc_basis_build_unsafe.argtypes = [vp, u64, vp]
+        L.orc_basis_adopt_lazy.argtypes = [vp, u64, vp]
+        L.orc_basis_build_range.restype = u64
+        L.orc_basis_build_range.argtypes = [vp, u64, u64, u64, vp, vp]
+        L.orc_sector_candidates.restype = u64
+        L.orc_sector_candidates.argtypes = [vp]
+        L.orc_operator_matmat_list.argtypes = [vp, ci, u64, vp, u64, vp, vp, C.POINTER(u64)]
         L.orc_basis_size.restype = u64
         L.orc_basis_size.argtypes = [vp]
         L.orc_basis_states.argtypes = [vp, vp]
@@ -148,6 +154,27 @@ class Basis:
             _check(lib().orc_basis_build_unsafe(self._h, len(r), r.ctypes.data))
         return self
 
+    def adopt_lazy(self, representatives):
+        """Adopt sorted representatives WITHOUT the O(N |G|) norm pass: norms are derived per use.
+        For bounded samples of sectors with ~10^9 states (bench.py parity checks at size)."""
+        r = np.ascontiguousarray(representatives, dtype=np.uint64)
+        _check(lib().orc_basis_adopt_lazy(self._h, len(r), r.ctypes.data))
+        return self
+
+    @property
+    def sector_candidates(self) -> int:
+        """number of candidate words of the sector (C(n, hw) or 2^n) the enumeration walks"""
+        return int(lib().orc_sector_candidates(self._h))
+
+    def build_range(self, rank_lo: int, rank_hi: int):
+        """Independent enumeration of the candidates of combinatorial rank [rank_lo, rank_hi):
+        returns (representatives found, first candidate word, one-past-last candidate word or 2^64-1)."""
+        cap = max(1, rank_hi - rank_lo)
+        out = np.zeros(cap, dtype=np.uint64)
+        rng = np.zeros(2, dtype=np.uint64)
+        cnt = int(lib().orc_basis_build_range(self._h, rank_lo, rank_hi, cap, out.ctypes.data, rng.ctypes.data))
+        return out[:cnt].copy(), int(rng[0]), int(rng[1])
+
     @property
     def number_states(self) -> int:
         return int(lib().orc_basis_size(self._h))
@@ -220,6 +247,15 @@ class Operator:
         _check(lib().orc_operator_matmat_rows(self._h, DTYPES[x.dtype], len(x), 1, x.ctypes.data, len(x), y.ctypes.data,
                                               len(y), C.byref(n_off), row_lo, row_hi, row_stride))
         return int(n_off.value)
+
+    def matmat_list(self, x: np.ndarray, rows: np.ndarray):
+        """(H x)[rows] for an explicit list of rows (1-D x); returns (values, off-diagonal elements visited)."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros(len(rows), dtype=x.dtype)
+        n_off = C.c_uint64(0)
+        _check(lib().orc_operator_matmat_list(self._h, DTYPES[x.dtype], len(x), x.ctypes.data, len(rows), rows.ctypes.data,
+                                              out.ctypes.data, C.byref(n_off)))
+        return out, int(n_off.value)
 
     def count_offdiag(self) -> int:
         """E = number of off-diagonal term applications with non-zero target norm."""

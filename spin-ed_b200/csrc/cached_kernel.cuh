@@ -117,23 +117,162 @@ template <bool HINT> __device__ __forceinline__ double2 load_x(double2 const* a,
   }
 }
 
-// y = H x from the cache: one warp per slice, coalesced index/code loads, read-only gathers of x,
-// accumulation in the stored (= matrix-free) order.  Elements are taken U at a time: all U index
-// and code loads are issued first, then the U gathers, then the U multiply-adds in order, so every
-// thread keeps U independent gathers in flight.
-// classes handled by pass `phase` (see cache_first_remote)
-__device__ __forceinline__ void phase_classes(CacheView const& c, int phase, u32& lo, u32& hi) {
-  u32 const fr = cache_first_remote(c.window);
-  if (phase == kPhaseAll) { lo = 0; hi = c.n_classes; }
-  else if (phase == kPhaseLocal) { lo = 0; hi = fr < c.n_classes ? fr : c.n_classes; }
-  else { lo = fr + (u32)phase - 2u; hi = lo + 1u; }
+// Predicated forms: a dead slot (past the end of the lane's list) issues no memory request at all
+// and yields zero.  Written as predicated PTX inside one volatile asm so that the compiler can
+// neither sink the load into a later conditional (which would serialise the gathers) nor
+// speculate it.
+template <bool HINT>
+__device__ __forceinline__ u32 load_stream_if(bool live, u32 const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  u32 v;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%2], %3;\n\t}"
+                 : "=r"(v) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.nc.u32 %0, [%2];\n\t}"
+                 : "=r"(v) : "r"((u32)live), "l"(a));
+  return v;
+#else
+  (void)pol;
+  return live ? *a : 0u;
+#endif
+}
+template <bool HINT>
+__device__ __forceinline__ u32 load_stream_if(bool live, dev_u8 const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  u32 v;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%2], %3;\n\t}"
+                 : "=r"(v) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.nc.u8 %0, [%2];\n\t}"
+                 : "=r"(v) : "r"((u32)live), "l"(a));
+  return v;
+#else
+  (void)pol;
+  return live ? (u32)*a : 0u;
+#endif
+}
+template <bool HINT>
+__device__ __forceinline__ u32 load_stream_if(bool live, dev_u16 const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  u32 v;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%2], %3;\n\t}"
+                 : "=r"(v) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u32 %0, 0;\n\t@p ld.global.nc.u16 %0, [%2];\n\t}"
+                 : "=r"(v) : "r"((u32)live), "l"(a));
+  return v;
+#else
+  (void)pol;
+  return live ? (u32)*a : 0u;
+#endif
+}
+template <bool HINT> __device__ __forceinline__ double load_x_if(bool live, double const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  double v;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.global.nc.L2::cache_hint.f64 %0, [%2], %3;\n\t}"
+                 : "=d"(v) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.global.nc.f64 %0, [%2];\n\t}"
+                 : "=d"(v) : "r"((u32)live), "l"(a));
+  return v;
+#else
+  (void)pol;
+  return live ? *a : 0.0;
+#endif
+}
+template <bool HINT> __device__ __forceinline__ double load_x_if(bool live, float const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  float v;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.global.nc.L2::cache_hint.f32 %0, [%2], %3;\n\t}"
+                 : "=f"(v) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [%2];\n\t}"
+                 : "=f"(v) : "r"((u32)live), "l"(a));
+  return (double)v;
+#else
+  (void)pol;
+  return live ? (double)*a : 0.0;
+#endif
+}
+template <bool HINT> __device__ __forceinline__ double2 load_x_if(bool live, double2 const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  double2 v;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t@p ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%3], %4;\n\t}"
+                 : "=d"(v.x), "=d"(v.y) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t@p ld.global.nc.v2.f64 {%0, %1}, [%3];\n\t}"
+                 : "=d"(v.x), "=d"(v.y) : "r"((u32)live), "l"(a));
+  return v;
+#else
+  (void)pol;
+  return live ? *a : double2{0.0, 0.0};
+#endif
+}
+template <bool HINT> __device__ __forceinline__ double2 load_x_if(bool live, float2 const* a, u64 pol) {
+#if defined(__CUDA_ARCH__)
+  float x, y;
+  if constexpr (HINT)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t@p ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%3], %4;\n\t}"
+                 : "=f"(x), "=f"(y) : "r"((u32)live), "l"(a), "l"(pol));
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t@p ld.global.nc.v2.f32 {%0, %1}, [%3];\n\t}"
+                 : "=f"(x), "=f"(y) : "r"((u32)live), "l"(a));
+  return make_double2(x, y);
+#else
+  (void)pol;
+  return live ? double2{(double)a->x, (double)a->y} : double2{0.0, 0.0};
+#endif
 }
 
-template <class T, int NB, class Code, bool SYM, bool HINT, int U>
-SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Traits<T>::cplx ? 1 : (U == 8 ? 5 : 6)) cached_matvec_kernel(CachedParams p) {
+// classes handled by pass `phase`: 0 -- all; 1 + c -- class c only
+__device__ __forceinline__ void phase_classes(CacheView const& c, int phase, u32& lo, u32& hi) {
+  if (phase == kPhaseAll) { lo = 0; hi = c.n_classes; }
+  else { lo = (u32)phase - 1u; hi = lo + 1u; }
+}
+
+// coefficient of a coded element: table entry (Re v, Im v, norm_s) times 1 / norm_r
+template <bool CPLX, bool SYM> struct Coeff;
+template <bool SYM> struct Coeff<false, SYM> {
+  typedef double W;
+  static __device__ __forceinline__ W get(double const* t, double inv_nr) {
+    double w = t[0];
+    if constexpr (SYM) w = w * (t[2] * inv_nr);
+    return w;
+  }
+};
+template <bool SYM> struct Coeff<true, SYM> {
+  typedef double2 W;
+  static __device__ __forceinline__ W get(double const* t, double inv_nr) {
+    double2 w = make_double2(t[0], t[1]);
+    if constexpr (SYM) {
+      double const scale = t[2] * inv_nr;
+      w.x *= scale;
+      w.y *= scale;
+    }
+    return w;
+  }
+};
+__device__ __forceinline__ void acc_add(double& a, double x) { a += x; }
+__device__ __forceinline__ void acc_add(double2& a, double2 x) { a.x += x.x; a.y += x.y; }
+
+// y = H x from the cache: one warp per slice, coalesced index (and code) loads, read-only gathers
+// of x.  Per source class a row first takes the elements that carry the default coefficient (front
+// of the class region, no code: their x entries are summed and multiplied once), then the coded
+// ones (back of the region, downwards; each looks its coefficient up).  Elements are taken U at a
+// time: all U index loads are issued first, then the U gathers, then the U accumulations in order,
+// so every thread keeps U independent gathers in flight.
+template <class T, int NB, class Code, bool SYM, bool HINT, int U, int MINB>
+SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Traits<T>::cplx ? 1 : MINB) cached_matvec_kernel(CachedParams p) {
   typedef Traits<T> TR;
   typedef typename TR::Acc Acc;
   constexpr bool CPLX = TR::cplx;
+  typedef Coeff<CPLX, SYM> CF;
   static_assert(NB == 1, "several columns go through cached_block_kernel");
   T const* __restrict__ x = static_cast<T const*>(p.x);
   T* __restrict__ y = static_cast<T*>(p.y);
@@ -146,39 +285,21 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Trait
     __syncthreads();
     table = s_table;
   }
-  // per warp: the window of x around the slice it is working on (CacheView, window class)
-  __shared__ T s_window[SPED_KERNEL_THREADS / 32][kWindowEntries];
-  u32 const warp_lanes = blockDim.x < 32u ? blockDim.x : 32u;  // 1 in the single-threaded host emulation
-  u32 const lane = threadIdx.x % warp_lanes;
-  T* const win = s_window[threadIdx.x / warp_lanes % (SPED_KERNEL_THREADS / 32)];
   u64 const pol_stream = l2_policy_evict_first<HINT>();
   u64 const pol_x = l2_policy_evict_last<HINT>();
   u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;  // this rank's shard inside the replicated x
   u64 const n_rows = p.ctx.dist.n_local;
   u32 cls_lo, cls_hi;
   phase_classes(p.cache, p.phase, cls_lo, cls_hi);
-  bool const use_window = p.cache.window != 0 && cls_lo == 0;
-  // warp-uniform loop over slices: i0 is the first row of the warp's slice (row_lo is a multiple of 32)
-  for (u64 i0 = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < p.row_hi; i0 += (u64)gridDim.x * blockDim.x) {
-    u64 const i = i0 + lane;
-    bool const active = i < p.row_hi;
-    if (use_window) {  // stage x[s - W, s + 32 + W) of this rank's shard, s = first row of the slice (zeros outside the shard)
-      u64 const sbase = i0 & ~(u64)31;  // == i0 on the GPU (blocks and row ranges are multiples of 32 rows)
-      __syncwarp();
-      for (u32 k = lane; k < kWindowEntries; k += warp_lanes) {
-        u64 const local = sbase + k - kWindow;  // wraps below zero: caught by the bound
-        T v{};
-        if (local < n_rows) v = x[self0 + local];
-        win[k] = v;
-      }
-      __syncwarp();
-    }
-    if (!active) continue;
+  bool const has_default = p.cache.default_code < p.cache.n_codes;
+  typename CF::W w_default{};
+  for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.row_hi; i += (u64)gridDim.x * blockDim.x) {
     double inv_nr = 1.0;
     if constexpr (SYM) {
       u64 const row = dist_local_to_global(p.ctx.dist, i);
       inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
     }
+    if (has_default) w_default = CF::get(table + 3 * p.cache.default_code, inv_nr);
     Acc acc;
     if (cls_lo == 0) {  // start from the diagonal term
       double dre = __ldg(p.diag_re + i);
@@ -193,121 +314,50 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Trait
     } else {  // continue from what the passes over the earlier classes stored
       acc = TR::load(y + i);
     }
-    u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
-    // the stored elements of this lane: per source class first the elements that carry the default
-    // coefficient (front of the class region, no code: their x entries are summed and multiplied
-    // once), then the coded ones (back of the region, downwards).  One copy of the loop body: a
-    // second inlined copy costs 15 registers and with them a resident block per SM.
-    u32 const width = (u32)((__ldg(p.cache.slice_off + (i >> 5) + 1) - __ldg(p.cache.slice_off + (i >> 5))) >> 5);
+    u64 const slice = i >> 5;
+    u64 const slice_base = __ldg(p.cache.slice_off + slice) + (i & 31);
+    u32 const width = (u32)((__ldg(p.cache.slice_off + slice + 1) - __ldg(p.cache.slice_off + slice)) >> 5);
 #pragma unroll 1
-    for (u32 seg = 2 * cls_lo; seg < 2 * cls_hi; ++seg) {
-      u32 const cls = seg >> 1;
-      bool const coded = (seg & 1u) != 0;
-      u32 const len = __ldg(p.cache.len + (u64)seg * n_rows + i);
-      u32 const lo = cls == 0 ? 0u : __ldg(p.cache.slice_start + 3 * (i >> 5) + (cls - 1));
-      u32 const hi = cls + 1 == p.cache.n_classes ? width : __ldg(p.cache.slice_start + 3 * (i >> 5) + cls);
-      // element j sits at slot lo + j (default coefficient) or hi - 1 - j (coded)
-      u32 const slot0 = coded ? hi - 1u : lo;
-      int const sstep = coded ? -1 : 1;
-      Acc part = acc_zero(Acc());  // this segment: sum of w x (coded) or of x (default coefficient)
-      if (use_window && cls == 0) {
-        // window class: the slot holds an offset into the staged window
-        for (u32 j = 0; j < len; ++j) {
-          u64 const pos = slice_base + (u64)(slot0 + (u32)(sstep * (int)j)) * 32;
-          u32 const off = load_stream<HINT>(cidx + pos, pol_stream);
-          Acc const xv = TR::to_acc(win[off]);
-          if constexpr (CPLX) {
-            double2 w = make_double2(1.0, 0.0);
-            if (coded) {
-              double const* t = table + 3 * load_stream<HINT>(ccode + pos, pol_stream);
-              w = make_double2(t[0], t[1]);
-              if constexpr (SYM) {
-                double const scale = t[2] * inv_nr;
-                w.x *= scale;
-                w.y *= scale;
-              }
-            }
-            acc_fma(part, w, xv);
-          } else {
-            double w = 1.0;
-            if (coded) {
-              double const* t = table + 3 * load_stream<HINT>(ccode + pos, pol_stream);
-              w = t[0];
-              if constexpr (SYM) w = w * (t[2] * inv_nr);
-            }
-            acc_fma(part, w, xv);
-          }
+    for (u32 cls = cls_lo; cls < cls_hi; ++cls) {
+      u32 const lo = cls == 0 ? 0u : __ldg(p.cache.slice_start + kClassStride * slice + (cls - 1));
+      u32 const hi = cls + 1 == p.cache.n_classes ? width : __ldg(p.cache.slice_start + kClassStride * slice + cls);
+      u32 const nd = __ldg(p.cache.len + (u64)(2 * cls) * n_rows + i);
+      u32 const nx = __ldg(p.cache.len + (u64)(2 * cls + 1) * n_rows + i);
+      // default coefficient: element j at slot lo + j
+      if (nd) {
+        Acc part = acc_zero(Acc());
+        u32 const* q = cidx + slice_base + (u64)lo * 32;
+#pragma unroll 1
+        for (u32 j0 = 0; j0 < nd; j0 += U, q += 32 * U) {
+          u32 idx[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) idx[u] = load_stream_if<HINT>(j0 + u < nd, q + 32 * u, pol_stream);
+          Acc xv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) xv[u] = load_x_if<HINT>(j0 + u < nd, x + idx[u], pol_x);  // dead slots: no request, zero
+#pragma unroll
+          for (int u = 0; u < U; ++u) acc_add(part, xv[u]);
         }
-      } else {
-        for (u32 j0 = 0; j0 < len; j0 += U) {
-          // `coded` is laundered through a volatile move so that the compiler does not unswitch the
-          // loop on it: two specialised copies of the body cost 30 registers (80 instead of 48)
-          u32 coded_i = seg & 1u;
-#if defined(__CUDA_ARCH__)
-          asm volatile("mov.u32 %0, %1;" : "=r"(coded_i) : "r"(seg & 1u));
-#endif
-          bool const coded_l = coded_i != 0;
+        acc_fma(acc, w_default, part);
+      }
+      // coded: element j at slot hi - 1 - j
+      if (nx) {
+        u64 const top = slice_base + (u64)(hi - 1u) * 32;
+#pragma unroll 1
+        for (u32 j0 = 0; j0 < nx; j0 += U) {
           u32 idx[U], code[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            bool const live = j0 + u < len;
-            u64 const pos = slice_base + (u64)(slot0 + (u32)(sstep * (int)(j0 + u))) * 32;
-            idx[u] = live ? load_stream<HINT>(cidx + pos, pol_stream) : (u32)(self0 + i);
-            code[u] = (live && coded_l) ? load_stream<HINT>(ccode + pos, pol_stream) : 0u;
+            bool const live = j0 + u < nx;
+            u64 const pos = top - (u64)(j0 + u) * 32;
+            idx[u] = load_stream_if<HINT>(live, cidx + pos, pol_stream);
+            code[u] = load_stream_if<HINT>(live, ccode + pos, pol_stream);
           }
           Acc xv[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) xv[u] = load_x<HINT>(x + idx[u], pol_x);  // dead slots re-read x[self]: an L1 hit
-          // one accumulate path for both kinds: coded elements look their coefficient up, the
-          // others add x itself (the common coefficient is applied once, after the loop)
+          for (int u = 0; u < U; ++u) xv[u] = load_x_if<HINT>(j0 + u < nx, x + idx[u], pol_x);
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (j0 + u < len) {
-              if constexpr (CPLX) {
-                double2 w = make_double2(1.0, 0.0);
-                if (coded_l) {
-                  double const* t = table + 3 * code[u];
-                  w = make_double2(t[0], t[1]);
-                  if constexpr (SYM) {
-                    double const scale = t[2] * inv_nr;
-                    w.x *= scale;
-                    w.y *= scale;
-                  }
-                }
-                acc_fma(part, w, xv[u]);
-              } else {
-                double w = 1.0;
-                if (coded_l) {
-                  double const* t = table + 3 * code[u];
-                  w = t[0];
-                  if constexpr (SYM) w = w * (t[2] * inv_nr);
-                }
-                acc_fma(part, w, xv[u]);
-              }
-            }
-          }
-        }
-      }
-      if (len) {  // acc += part (coded) or w_default * part
-        double const* t = table + 3 * p.cache.default_code;  // only dereferenced for a non-empty default segment
-        if constexpr (CPLX) {
-          double2 w = make_double2(1.0, 0.0);
-          if (!coded) {
-            w = make_double2(t[0], t[1]);
-            if constexpr (SYM) {
-              double const scale = t[2] * inv_nr;
-              w.x *= scale;
-              w.y *= scale;
-            }
-          }
-          acc_fma(acc, w, part);
-        } else {
-          double w = 1.0;
-          if (!coded) {
-            w = t[0];
-            if constexpr (SYM) w = w * (t[2] * inv_nr);
-          }
-          acc_fma(acc, w, part);
+          for (int u = 0; u < U; ++u) acc_fma(acc, CF::get(table + 3 * code[u], inv_nr), xv[u]);  // dead slots add w * 0
         }
       }
     }
@@ -384,11 +434,65 @@ inline void load_xrow(T const* a, u64, A (&out)[NB]) {
 }
 #endif
 
+// scalars of a loaded block row -> accumulator-typed entries
+template <int NB, class S> __device__ __forceinline__ void unpack_row(S const* v, double (&out)[NB]) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k) out[k] = (double)v[k];
+}
+template <int NB, class S> __device__ __forceinline__ void unpack_row(S const* v, double2 (&out)[NB]) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k) out[k] = make_double2((double)v[2 * k], (double)v[2 * k + 1]);
+}
+
+// predicated block-row load: a dead slot issues no request and yields zeros
+template <class T> struct IsSingle { static constexpr bool value = false; };
+template <> struct IsSingle<float> { static constexpr bool value = true; };
+template <> struct IsSingle<float2> { static constexpr bool value = true; };
+
+template <int NB, class T, class A>
+__device__ __forceinline__ void load_xrow_if(bool live, T const* a, u64 pol, A (&out)[NB]) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (IsSingle<T>::value) {
+    constexpr int NF = (int)(sizeof(T) * NB / 4);  // 2, 4 or 8 floats
+    float v[NF];
+    float const* f = reinterpret_cast<float const*>(a);
+    if constexpr (NF == 2) {
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+                   "@p ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%3], %4;\n\t}"
+                   : "=f"(v[0]), "=f"(v[1]) : "r"((u32)live), "l"(f), "l"(pol));
+    } else {
+#pragma unroll
+      for (int h = 0; h < NF / 4; ++h)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+                     "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+                     "@p ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%5], %6;\n\t}"
+                     : "=f"(v[4 * h]), "=f"(v[4 * h + 1]), "=f"(v[4 * h + 2]), "=f"(v[4 * h + 3])
+                     : "r"((u32)live), "l"(f + 4 * h), "l"(pol));
+    }
+    unpack_row<NB>(v, out);
+  } else {
+    constexpr int ND = (int)(sizeof(T) * NB / 8);  // 2, 4 or 8 doubles, two per load
+    double v[ND];
+    double const* d = reinterpret_cast<double const*>(a);
+#pragma unroll
+    for (int h = 0; h < ND / 2; ++h)
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+                   "@p ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%3], %4;\n\t}"
+                   : "=d"(v[2 * h]), "=d"(v[2 * h + 1]) : "r"((u32)live), "l"(d + 2 * h), "l"(pol));
+    unpack_row<NB>(v, out);
+  }
+#else
+  (void)pol;
+  for (int k = 0; k < NB; ++k) out[k] = live ? Traits<T>::load(a + k) : acc_zero(A());
+#endif
+}
+
 template <class T, int NB, class Code, bool SYM, int U>
-SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) cached_block_kernel(CachedParams p) {
+SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, (sizeof(T) * NB <= 16 ? 5 : 4)) cached_block_kernel(CachedParams p) {
   typedef Traits<T> TR;
   typedef typename TR::Acc Acc;
   constexpr bool CPLX = TR::cplx;
+  typedef Coeff<CPLX, SYM> CF;
   T const* __restrict__ xt = static_cast<T const*>(p.x);  // interleaved: entry (pos, c) at pos * NB + c
   T* __restrict__ y = static_cast<T*>(p.y);
   u32 const* __restrict__ cidx = p.cache.idx;
@@ -404,14 +508,19 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) cache
   u64 const pol_x = l2_policy_evict_last<kBlockHint>();
   u64 const self0 = (u64)p.ctx.dist.rank * p.ctx.dist.chunk;
   u64 const n_rows = p.ctx.dist.n_local;
+  u32 cls_lo, cls_hi;
+  phase_classes(p.cache, p.phase, cls_lo, cls_hi);
+  bool const has_default = p.cache.default_code < p.cache.n_codes;
+  typename CF::W w_default{};
   for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.row_hi; i += (u64)gridDim.x * blockDim.x) {
     double inv_nr = 1.0;
     if constexpr (SYM) {
       u64 const row = dist_local_to_global(p.ctx.dist, i);
       inv_nr = 1.0 / __ldg(p.ctx.norm_table + __ldg(p.ctx.index.stab + row));
     }
+    if (has_default) w_default = CF::get(table + 3 * p.cache.default_code, inv_nr);
     Acc acc[NB];
-    {
+    if (cls_lo == 0) {
       Acc xv[NB];
       load_xrow<NB>(xt + (self0 + i) * NB, pol_x, xv);
       double const dre = __ldg(p.diag_re + i);
@@ -422,54 +531,59 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) cache
         if constexpr (CPLX) acc_fma(acc[c], make_double2(dre, dim_), xv[c]);
         else acc_fma(acc[c], dre, xv[c]);
       }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NB; ++c) acc[c] = c < (int)p.ncols ? TR::load(y + (u64)c * p.ys + i) : acc_zero(Acc());
     }
-    u64 const slice_base = __ldg(p.cache.slice_off + (i >> 5)) + (i & 31);
-    u32 const width = (u32)((__ldg(p.cache.slice_off + (i >> 5) + 1) - __ldg(p.cache.slice_off + (i >> 5))) >> 5);
+    u64 const slice = i >> 5;
+    u64 const slice_base = __ldg(p.cache.slice_off + slice) + (i & 31);
+    u32 const width = (u32)((__ldg(p.cache.slice_off + slice + 1) - __ldg(p.cache.slice_off + slice)) >> 5);
 #pragma unroll 1
-    for (u32 seg = 0; seg < 2 * p.cache.n_classes; ++seg) {  // (class, default-coefficient | coded), see CacheView
-      u32 const cls = seg >> 1;
-      bool const coded = (seg & 1u) != 0;
-      u32 const len = __ldg(p.cache.len + (u64)seg * n_rows + i);
-      u32 const lo = cls == 0 ? 0u : __ldg(p.cache.slice_start + 3 * (i >> 5) + (cls - 1));
-      u32 const hi = cls + 1 == p.cache.n_classes ? width : __ldg(p.cache.slice_start + 3 * (i >> 5) + cls);
-      // window class: the slot holds an offset into the slice's window; here it is turned back into a position
-      bool const windowed = cls == 0 && p.cache.window != 0;
-      u32 const window_base = (u32)(self0 + (i & ~(u64)31)) - kWindow;
-      long long const step = coded ? -32ll : 32ll;
-      u64 const base = slice_base + (u64)(coded ? hi - 1u : lo) * 32;
-      for (u32 j0 = 0; j0 < len; j0 += U) {
-        u32 idx[U], code[U];
+    for (u32 cls = cls_lo; cls < cls_hi; ++cls) {
+      u32 const lo = cls == 0 ? 0u : __ldg(p.cache.slice_start + kClassStride * slice + (cls - 1));
+      u32 const hi = cls + 1 == p.cache.n_classes ? width : __ldg(p.cache.slice_start + kClassStride * slice + cls);
+      u32 const nd = __ldg(p.cache.len + (u64)(2 * cls) * n_rows + i);
+      u32 const nx = __ldg(p.cache.len + (u64)(2 * cls + 1) * n_rows + i);
+      if (nd) {  // default coefficient: element j at slot lo + j; sum the block rows, multiply once
+        Acc part[NB];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          bool const live = j0 + u < len;
-          u64 const pos = (u64)((long long)base + step * (long long)(j0 + u));
-          idx[u] = live ? load_stream<kBlockHint>(cidx + pos, pol_stream) + (windowed ? window_base : 0u) : (u32)(self0 + i);
-          code[u] = live ? (coded ? load_stream<kBlockHint>(ccode + pos, pol_stream) : p.cache.default_code) : 0u;
+        for (int c = 0; c < NB; ++c) part[c] = acc_zero(Acc());
+        u32 const* q = cidx + slice_base + (u64)lo * 32;
+#pragma unroll 1
+        for (u32 j0 = 0; j0 < nd; j0 += U, q += 32 * U) {
+          u32 idx[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) idx[u] = load_stream_if<kBlockHint>(j0 + u < nd, q + 32 * u, pol_stream);
+          Acc xv[U][NB];
+#pragma unroll
+          for (int u = 0; u < U; ++u) load_xrow_if<NB>(j0 + u < nd, xt + (u64)idx[u] * NB, pol_x, xv[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) acc_add(part[c], xv[u][c]);
+          }
         }
-        Acc xv[U][NB];
 #pragma unroll
-        for (int u = 0; u < U; ++u) load_xrow<NB>(xt + (u64)idx[u] * NB, pol_x, xv[u]);
-        // NOTE (SASS, not yet measured): ptxas software-pipelines this loop two gathers deep at 40
-        // registers (6 blocks/SM) instead of issuing all U first; a warp fence is hoisted above the
-        // gathers and a block fence costs a MEMBAR.SC -- to be tuned on hardware.
-        // branch-free: a dead slot multiplies x[self] by zero, so that the gathers above cannot be
-        // sunk into per-element conditionals (which serialises them)
+        for (int c = 0; c < NB; ++c) acc_fma(acc[c], w_default, part[c]);
+      }
+      if (nx) {  // coded: element j at slot hi - 1 - j
+        u64 const top = slice_base + (u64)(hi - 1u) * 32;
+#pragma unroll 1
+        for (u32 j0 = 0; j0 < nx; j0 += U) {
+          u32 idx[U], code[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          bool const live = j0 + u < len;
-          double const* t = table + 3 * code[u];
-          if constexpr (CPLX) {
-            double2 w = make_double2(live ? t[0] : 0.0, live ? t[1] : 0.0);
-            if constexpr (SYM) {
-              double const scale = t[2] * inv_nr;
-              w.x *= scale;
-              w.y *= scale;
-            }
+          for (int u = 0; u < U; ++u) {
+            bool const live = j0 + u < nx;
+            u64 const pos = top - (u64)(j0 + u) * 32;
+            idx[u] = load_stream_if<kBlockHint>(live, cidx + pos, pol_stream);
+            code[u] = load_stream_if<kBlockHint>(live, ccode + pos, pol_stream);
+          }
+          Acc xv[U][NB];
 #pragma unroll
-            for (int c = 0; c < NB; ++c) acc_fma(acc[c], w, xv[u][c]);
-          } else {
-            double w = live ? t[0] : 0.0;
-            if constexpr (SYM) w = w * (t[2] * inv_nr);
+          for (int u = 0; u < U; ++u) load_xrow_if<NB>(j0 + u < nx, xt + (u64)idx[u] * NB, pol_x, xv[u]);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {  // dead slots add w * 0
+            typename CF::W const w = CF::get(table + 3 * code[u], inv_nr);
 #pragma unroll
             for (int c = 0; c < NB; ++c) acc_fma(acc[c], w, xv[u][c]);
           }
@@ -481,6 +595,5 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) cache
       if (c < (int)p.ncols) TR::store(y + (u64)c * p.ys + i, acc[c]);
   }
 }
-
 
 }  // namespace sped

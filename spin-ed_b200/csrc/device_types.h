@@ -115,60 +115,36 @@ struct MatvecParams {
 // class 2 -- the other ranks (second round; absent when all peers fit in one round).  Inside a slice
 // class c occupies slots [start_c, start_c+1) for every lane, so every class is read coalesced; the
 // streaming kernel runs once per class, each pass overlapping the transfer the next one waits for.
-constexpr int kMaxClasses = 4;
-// Window class (optional, class 0 when present): a warp walks the 32 consecutive local rows of a
-// slice, and a fifth (6x6) to two fifths (chains) of their elements gather from local rows within
-// a few hundred rows of the slice itself.  The streaming kernel stages x[32 s - W, 32 s + 32 + W)
-// (local indices) in shared memory once per slice and serves these elements from there: a handful
-// of bank-conflict wavefronts instead of ~13 L1 lines per warp gather.  Their slots hold the offset
-// into the window instead of a position.
-constexpr u32 kWindow = 128;                     // W
-constexpr u32 kWindowEntries = 32 + 2 * kWindow;
+constexpr int kMaxClasses = 3;
+constexpr int kClassStride = kMaxClasses - 1;  // slice_start entries per slice
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
-  u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout);
-                         // window class: offset into the slice's window
+  u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
   void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
   dev_u16 const* len;    // [2 * n_classes][local rows]: per source class the elements that carry the
                          // default coefficient (no code is read for them), then the coded ones
-  u32 const* slice_start;  // [n_slices][3] first slot of classes 1, 2, 3; null with one class
+  u32 const* slice_start;  // [n_slices][kClassStride] first slot of classes 1, 2; null with one class
   double const* table;   // [n_codes][3]: (Re v, Im v, norm_s) with v = M[a][b] * chi(g')
   u64 n_slices;
   int code_wide;         // 1: u16 codes
   u32 n_codes;           // entries of `table`
-  u32 n_classes;         // [window] local [remote near] [remote far]: 1 .. 4
+  u32 n_classes;         // local [remote near] [remote far]: 1 .. 3
   u32 near;              // first remote class = owners rank+1 .. rank+near (mod world)
   u32 default_code;      // the coefficient almost every element carries (first matrix value, chi = 1,
                          // trivial stabiliser).  Inside its class region [start_c, start_c+1) a row keeps
                          // these elements from the front, s = start_c + j, and the others -- with
                          // their code -- from the back, s = start_c+1 - 1 - j ("two-ended"), so one
                          // traversal fills both without knowing their numbers in advance.
-  u32 window;            // 1: class 0 is the window class
   u32 rounds;            // exchange rounds = remote classes (0 with one rank)
-  u32 pad_;
 };
 
-// first remote class / classes handled by pass `phase` (0: all; 1: everything this rank owns the
-// sources of; 2, 3: first / second exchange round)
-SPED_DIST_FN u32 cache_first_remote(u32 window) { return window ? 2u : 1u; }
-
-// Class of the entry at position `pos` of the replicated vector for local row i of rank d.rank;
-// *window_offset receives the offset into the slice's window for the window class.
-SPED_DIST_FN u32 dist_source_class(RowDist const& d, u64 pos, u64 i, u32 window, u32 rounds, u32 near, u32* window_offset) {
+// Class of the entry at position `pos` of the replicated vector for the rows of rank d.rank:
+// 0 -- this rank owns it; 1 -- one of the `near` next ranks does (first exchange round); 2 -- the rest.
+SPED_DIST_FN u32 dist_source_class(RowDist const& d, u64 pos, u32 rounds, u32 near) {
   u32 const owner = d.world == 1 ? 0u : (u32)(pos / d.chunk);
-  if (owner == d.rank) {
-    if (window) {
-      u64 const local = pos - (u64)d.rank * d.chunk;
-      u64 const off = local + kWindow - (i & ~(u64)31);  // wraps to a huge value when below the window
-      if (off < kWindowEntries) {
-        *window_offset = (u32)off;
-        return 0u;
-      }
-    }
-    return window ? 1u : 0u;
-  }
+  if (owner == d.rank) return 0u;
   u32 const dd = owner > d.rank ? owner - d.rank : owner + d.world - d.rank;
-  return cache_first_remote(window) + ((rounds == 2 && dd > near) ? 1u : 0u);
+  return 1u + ((rounds == 2 && dd > near) ? 1u : 0u);
 }
 
 struct FillParams {
@@ -180,13 +156,11 @@ struct FillParams {
   dev_u16* len;            // [2 * n_classes][local rows] (see CacheView)
   u32 default_code;
   u32 pad1_;
-  u32 const* slice_start;  // several classes, fill pass: [n_slices][3] (see CacheView); null otherwise
+  u32 const* slice_start;  // several classes, fill pass: [n_slices][kClassStride] (see CacheView); null otherwise
   int count_only;          // exact class sizes wanted: first pass, only `len` is written
   u32 n_classes;
   u32 near;
-  u32 window;              // see CacheView
   u32 rounds;
-  u32 pad0_;
   dev_u16 const* hid_map;  // [pool_size] matrix element -> distinct-value id
   dev_u16 const* sid_map;  // [|G'| + 1] stabiliser size -> id (null for the trivial group)
   dev_u16 const* pid_map;  // [denom] phase numerator -> id among the phases that occur (null: trivial group)

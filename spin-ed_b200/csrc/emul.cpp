@@ -6,13 +6,15 @@
 // so that slot arithmetic, source classes and summation logic can be checked against the oracle
 // without a GPU (tests/test_emulation.py).  The orchestration around the kernels (code maps,
 // slice widths, offsets) mirrors Operator::cache_usable with std::vector buffers.  This is a
-// verification hook (include/sped_selftest.h), not a compute path: nothing in the product calls it.
+// verification hook built into the test-only library libsped_emul.so (emul.h); libsped.so neither
+// contains nor calls it.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <type_traits>
 #include <vector>
 
+#include "emul.h"
 #include "internal.h"
 
 // ---- shims for the device built-ins (one thread, one block) ----
@@ -170,13 +172,12 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
     table[3 * c + 2] = pr.sym ? pr.norm_table[cm.sid_stab[sid]] : 1.0;
   }
   u32 const rounds = (u32)exchange_rounds(d.world);
-  u32 const window = window_enabled() ? 1u : 0u;
-  u32 const n_classes = window + 1u + rounds;
+  u32 const n_classes = 1u + rounds;
   u32 const near = exchange_near(d.world);
   bool const wide = cm.n_codes > 256;
   u64 const n_slices = (n_local + 31) / 32;
   std::vector<std::uint16_t> len(std::max<u64>(n_local, 1) * 2 * n_classes, 0);
-  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_start(std::max<u64>(n_slices, 1) * 3, 0);
+  std::vector<u32> widths(std::max<u64>(n_slices, 1), 0), slice_start(std::max<u64>(n_slices, 1) * kClassStride, 0);
   int overflow = 0;
   FillParams fp{};
   fp.ctx = pr.ctx;
@@ -184,7 +185,6 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   fp.len = len.data();
   fp.n_classes = n_classes;
   fp.near = near;
-  fp.window = window;
   fp.rounds = rounds;
   fp.default_code = cm.default_code;
   fp.hid_map = cm.hid_map.data();
@@ -198,13 +198,12 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
     fp.count_only = 1;
     pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
     for (u64 s = 0; s < n_slices; ++s) {  // class_width_kernel
-      u32 w[kMaxClasses] = {0, 0, 0, 0};
+      u32 w[kMaxClasses] = {0, 0, 0};
       for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i)
         for (u32 c = 0; c < n_classes; ++c) w[c] = std::max<u32>(w[c], len[(u64)(2 * c) * n_local + i]);
-      widths[s] = w[0] + w[1] + w[2] + w[3];
-      slice_start[3 * s] = w[0];
-      slice_start[3 * s + 1] = w[0] + w[1];
-      slice_start[3 * s + 2] = w[0] + w[1] + w[2];
+      widths[s] = w[0] + w[1] + w[2];
+      slice_start[kClassStride * s] = w[0];
+      slice_start[kClassStride * s + 1] = w[0] + w[1];
     }
     fp.count_only = 0;
     fp.slice_start = slice_start.data();
@@ -221,13 +220,8 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
         }
         mx = std::max(mx, ub);
       }
-      u32 const ws = window ? window_slots() : 0u;  // guessed width of the window region
-      widths[s] = mx + ws;
-      slice_start[3 * s] = ws;
-      slice_start[3 * s + 1] = mx + ws;
-      slice_start[3 * s + 2] = mx + ws;
+      widths[s] = mx;
     }
-    if (window) fp.slice_start = slice_start.data();
   }
   std::vector<u64> slice_off(n_slices + 1, 0);
   for (u64 s = 0; s < n_slices; ++s) slice_off[s + 1] = slice_off[s] + 32ull * widths[s];
@@ -246,19 +240,15 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
       elements += len[(u64)seg * n_local + i];
       if (!(seg & 1)) dflt += len[(u64)seg * n_local + i];
     }
-  u64 windowed = 0;
-  if (window)
-    for (u64 i = 0; i < n_local; ++i) windowed += len[i] + len[n_local + i];
   stats[0] = slots;
   stats[1] = elements;
   stats[2] = dflt;
   stats[3] = n_classes;
-  stats[4] = windowed;
 
   // ---- streaming kernel: all classes in one pass, then class by class ----
   CachedParams cp{};
   cp.cache = CacheView{slice_off.data(), idx.data(), code.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,
-                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, window, rounds, 0u};
+                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, rounds};
   cp.ctx = pr.ctx;
   cp.diag_re = pr.diag_re.data();
   cp.diag_im = cplx_diag ? pr.diag_im.data() : nullptr;
@@ -272,10 +262,10 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   auto launch = [&](T* y, int phase) {
     cp.y = y;
     cp.phase = phase;
-    if (wide && pr.sym) cached_matvec_kernel<T, 1, std::uint16_t, true, false, 8>(cp);
-    else if (wide) cached_matvec_kernel<T, 1, std::uint16_t, false, false, 8>(cp);
-    else if (pr.sym) cached_matvec_kernel<T, 1, std::uint8_t, true, false, 8>(cp);
-    else cached_matvec_kernel<T, 1, std::uint8_t, false, false, 8>(cp);
+    if (wide && pr.sym) cached_matvec_kernel<T, 1, std::uint16_t, true, false, 4, 6>(cp);
+    else if (wide) cached_matvec_kernel<T, 1, std::uint16_t, false, false, 4, 6>(cp);
+    else if (pr.sym) cached_matvec_kernel<T, 1, std::uint8_t, true, false, 4, 6>(cp);
+    else cached_matvec_kernel<T, 1, std::uint8_t, false, false, 4, 6>(cp);
   };
   if (n_local) {
     launch(y_all, 0);
@@ -296,7 +286,7 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
     cp.phase = 0;
     auto go = [&](auto nbtag) {
       constexpr int NB = decltype(nbtag)::value;
-      constexpr int U = NB == 2 ? 8 : 4;
+      constexpr int U = NB == 2 ? 4 : 2;
       if (wide && pr.sym) cached_block_kernel<T, NB, std::uint16_t, true, U>(cp);
       else if (wide) cached_block_kernel<T, NB, std::uint16_t, false, U>(cp);
       else if (pr.sym) cached_block_kernel<T, NB, std::uint8_t, true, U>(cp);

@@ -219,8 +219,8 @@ struct Operator {
   DeviceBuffer<unsigned char> c_code;  // u8 or u16 per slot
   int c_code_wide = 0;
   DeviceBuffer<std::uint16_t> c_len;   // [2 * c_classes][local rows]: default-coefficient / coded elements per source class
-  DeviceBuffer<u32> c_slice_start;     // [slices][3] first slot of classes 1, 2, 3 (several classes only)
-  u32 c_classes = 1, c_near = 0, c_default_code = 0, c_window = 0, c_rounds = 0;
+  DeviceBuffer<u32> c_slice_start;     // [slices][kClassStride] first slot of classes 1, 2 (several classes only)
+  u32 c_classes = 1, c_near = 0, c_default_code = 0, c_rounds = 0;
   DeviceBuffer<double> c_table;
   u64 c_slices = 0, c_slots = 0, cache_bytes = 0;
   double cache_build_seconds = 0;
@@ -257,8 +257,6 @@ struct Operator {
 
 int exchange_rounds(unsigned world);  // opcache.cu
 unsigned exchange_near(unsigned world);
-bool window_enabled();                // opcache.cu
-unsigned window_slots();
 
 // Code maps of the operator cache (opcache.cu, build_code_maps)
 struct CodeMaps {

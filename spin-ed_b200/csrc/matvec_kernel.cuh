@@ -232,15 +232,15 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
     u64 base = 0;
-    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u, 0u};  // first slot of each class; start[c >= n_classes] = width
+    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u};  // first slot of each class; start[c >= n_classes] = width
     if (!count_only) {
       base = __ldg(p.slice_off + slice) + (i & 31);
       u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
-      for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(p.slice_start + 3 * slice + (c - 1)) : width;
+      for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(p.slice_start + kClassStride * slice + (c - 1)) : width;
     }
     // per class: cd = elements with the default coefficient (stored from the front of the class
     // region), cx = coded elements (stored from its back)
-    u32 cd[kMaxClasses] = {0u, 0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u, 0u};
+    u32 cd[kMaxClasses] = {0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u};
     for_each_transition(terms, r, [&](DevBond const& bd, u32 a, u32 b, u64 rp) {
       u64 rep = rp;
       int ph = 0;
@@ -248,11 +248,7 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u64 idx = lookup_index(ix, rep);
       if (idx == ~(u64)0) return;
       u64 const pos = dist_global_to_pos(dist, idx);  // stored ready for the gather
-      u32 woff = 0;
-      u32 cls = dist_source_class(dist, pos, i, p.window, p.rounds, p.near, &woff);
-      // a full window region (its width is a guess when the classes are not counted first) sends
-      // the element to the plain local class, where every local source can live
-      if (!count_only && cls == 0 && p.window && cd[0] + cx[0] >= start[1] - start[0]) cls = 1;
+      u32 const cls = dist_source_class(dist, pos, p.rounds, p.near);
       u32 hid = p.hid_map[bd.moff + a * (1u << bd.k) + b];
       u32 sid = SYM ? (u32)__ldg(p.sid_map + __ldg(ix.stab + idx)) : 0u;
       u32 const pid = SYM ? (u32)__ldg(p.pid_map + ph) : 0u;
@@ -267,7 +263,7 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
         return;
       }
       u64 const at = base + (u64)(dflt ? lo + nd : hi - 1u - nx) * 32;
-      p.idx[at] = (cls == 0 && p.window) ? woff : (u32)pos;
+      p.idx[at] = (u32)pos;
       if (!dflt) {
         if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
         else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;

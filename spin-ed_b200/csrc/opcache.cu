@@ -31,8 +31,7 @@ namespace {
 
 // Upper bound of the row lengths (transitions with a non-zero matrix element, whether or not the
 // target survives the projection) and its maximum over each slice.
-__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths, u32 window_slots,
-                                                               u32* slice_start) {
+__global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, TermsView terms_g, u32* widths) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(terms_g, smem);
   u64 const n_local = ctx.dist.n_local;
@@ -50,16 +49,7 @@ __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, T
       }
     }
     u32 mx = __reduce_max_sync(0xffffffffu, ub);
-    if ((i & 31) == 0) {
-      // window class in front (its width is a guess: what does not fit goes to the local class,
-      // which is wide enough for every element of the row), then the local class
-      widths[i >> 5] = mx + window_slots;
-      if (slice_start) {
-        slice_start[3 * (i >> 5)] = window_slots;
-        slice_start[3 * (i >> 5) + 1] = mx + window_slots;
-        slice_start[3 * (i >> 5) + 2] = mx + window_slots;
-      }
-    }
+    if ((i & 31) == 0) widths[i >> 5] = mx;
   }
 }
 
@@ -69,17 +59,16 @@ __global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t con
                                                                u32* widths, u32* slice_start) {
   u64 const n_padded = (n_local + 31) & ~(u64)31;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
-    u32 w[kMaxClasses] = {0u, 0u, 0u, 0u};
+    u32 w[kMaxClasses] = {0u, 0u, 0u};
 #pragma unroll
     for (u32 c = 0; c < (u32)kMaxClasses; ++c) {
       u32 v = (c < n_classes && i < n_local) ? len[(u64)(2 * c) * n_local + i] : 0u;  // count pass: class totals
       w[c] = __reduce_max_sync(0xffffffffu, v);
     }
     if ((i & 31) == 0) {
-      widths[i >> 5] = w[0] + w[1] + w[2] + w[3];
-      slice_start[3 * (i >> 5)] = w[0];
-      slice_start[3 * (i >> 5) + 1] = w[0] + w[1];
-      slice_start[3 * (i >> 5) + 2] = w[0] + w[1] + w[2];
+      widths[i >> 5] = w[0] + w[1] + w[2];
+      slice_start[kClassStride * (i >> 5)] = w[0];
+      slice_start[kClassStride * (i >> 5) + 1] = w[0] + w[1];
     }
   }
 }
@@ -154,13 +143,12 @@ __global__ void table_kernel(double const* values_re, double const* values_im, d
 namespace sped {
 namespace {
 
-// SPED_CACHED_VARIANT (tuning knob, default = the measured best): bit 0 cache-policy loads,
-// bit 1 eight (instead of four) elements in flight per thread.  Measured on B200 (6x6, f64):
-// 0: 2.10 ms, 1: 1.90 ms, 2: 1.83 ms, 3: 1.66 ms; sixteen in flight (86 registers): 2.00 ms.
+// SPED_CACHED_VARIANT (tuning knob, default = the measured best): bit 0 cache-policy loads; bits 1..3
+// elements in flight per thread / resident blocks per SM the register budget is set for.
 int cached_variant() {
   static int v = [] {
     char const* e = std::getenv("SPED_CACHED_VARIANT");
-    return e && *e ? std::atoi(e) : 3;
+    return e && *e ? std::atoi(e) : 1;
   }();
   return v;
 }
@@ -185,11 +173,17 @@ void launch_cached_kernel(CachedParams const& p, cudaStream_t s) {
 
 template <class T, int NB, class Code, bool SYM>
 void launch_cached_variant(CachedParams const& p, cudaStream_t s) {
-  switch (cached_variant() & 3) {
-    case 0: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 4>>(p, s); break;
-    case 1: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4>>(p, s); break;
-    case 2: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 8>>(p, s); break;
-    default: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8>>(p, s); break;
+  switch (cached_variant()) {
+    case 0: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 4, 6>>(p, s); break;
+#if defined(SPED_CACHED_SWEEP)  // tuning builds only (tools/sweep_cached.sh): (elements in flight, blocks per SM)
+    case 3: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 5>>(p, s); break;
+    case 5: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 8>>(p, s); break;
+    case 7: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 2, 8>>(p, s); break;
+    case 9: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 6>>(p, s); break;
+    case 11: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 3, 7>>(p, s); break;
+    case 13: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 7>>(p, s); break;
+#endif
+    default: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 6, 5>>(p, s); break;
   }
 }
 
@@ -208,7 +202,7 @@ void launch_block(CachedParams const& p, T const* x, u64 xs, u64 n_entries, T* s
   KERNEL_LAUNCHED();
   CachedParams q = p;
   q.x = scratch;
-  constexpr int U = NB == 2 ? 8 : 4;  // 32 accumulator-typed values in flight either way
+  constexpr int U = NB == 2 ? 4 : 2;
   bool const wide = p.cache.code_wide != 0, sym = p.sym != 0;
   if (wide && sym) launch_cached_kernel<cached_block_kernel<T, NB, std::uint16_t, true, U>>(q, s);
   else if (wide) launch_cached_kernel<cached_block_kernel<T, NB, std::uint16_t, false, U>>(q, s);
@@ -335,18 +329,6 @@ char const* build_code_maps(Operator const& op, CodeMaps& out) {
   return nullptr;
 }
 
-// SPED_WINDOW=0 switches the window class off; SPED_WINDOW_SLOTS sets its width per lane when the
-// classes are not counted first (one rank): window-eligible elements beyond it go to the local class.
-bool window_enabled() {
-  char const* e = std::getenv("SPED_WINDOW");
-  return !(e && e[0] == '0');
-}
-unsigned window_slots() {
-  char const* e = std::getenv("SPED_WINDOW_SLOTS");
-  int v = e && *e ? std::atoi(e) : 16;
-  return (unsigned)std::max(1, std::min(v, 64));
-}
-
 // Peers of the first exchange round: ranks r+1 .. r+near (a function of the world size and the
 // environment only, like exchange_rounds: every rank must agree on who talks in which round).
 unsigned exchange_near(unsigned world) { return exchange_rounds(world) == 2 ? world / 2 : world - 1; }
@@ -361,7 +343,6 @@ void Operator::drop_cache() {
   c_slice_start.release();
   c_classes = 1;
   c_near = 0;
-  c_window = 0;
   c_rounds = 0;
   c_table.release();
   c_slices = c_slots = cache_bytes = 0;
@@ -417,8 +398,7 @@ bool Operator::cache_usable() {
   // source classes (see CacheView): local / peers of the first exchange round / of the second
   u32 const world = dist.world;
   c_rounds = (u32)exchange_rounds(world);
-  c_window = window_enabled() ? 1u : 0u;
-  c_classes = c_window + 1 + c_rounds;
+  c_classes = 1 + c_rounds;
   c_near = exchange_near(world);  // 8 ranks: 4 peers in the first round, 3 in the second
   bool const two = c_rounds > 0;  // several ranks: exact class sizes from a counting traversal
   MatvecParams mp = operator_params(*this);
@@ -432,7 +412,6 @@ bool Operator::cache_usable() {
   fp.len = c_len.ptr;
   fp.n_classes = c_classes;
   fp.near = c_near;
-  fp.window = c_window;
   fp.rounds = c_rounds;
   c_default_code = cm_.default_code;
   fp.default_code = c_default_code;
@@ -475,20 +454,14 @@ bool Operator::cache_usable() {
   if (two) {
     fp.count_only = 1;
     launch_fill();
-    c_slice_start.alloc(c_slices * 3);
+    c_slice_start.alloc(c_slices * kClassStride);
     class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, d_widths.ptr,
                                                                                  c_slice_start.ptr);
     fp.count_only = 0;
     fp.slice_start = c_slice_start.ptr;
   } else {
     if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    if (c_window) {
-      c_slice_start.alloc(c_slices * 3);
-      fp.slice_start = c_slice_start.ptr;
-    }
-    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr,
-                                                                                 c_window ? window_slots() : 0u,
-                                                                                 c_window ? c_slice_start.ptr : nullptr);
+    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_widths.ptr);
   }
   KERNEL_LAUNCHED();
   c_slice_off.alloc(c_slices + 1);
@@ -496,7 +469,7 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 20 : 8) + n_codes * 24;
+  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 16 : 8) + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
@@ -546,7 +519,7 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
   p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_slice_start.ptr, c_table.ptr, c_slices,
-                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_window, c_rounds, 0u};
+                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_rounds};
   p.phase = phase;
   p.beside_transfer = beside_transfer ? 1 : 0;
   p.ctx = mp.ctx;

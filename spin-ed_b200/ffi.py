@@ -123,8 +123,27 @@ SIGNATURES = {
     "sped_selftest_burnside": (_ci, [_vp, C.POINTER(_u64)]),
     "sped_selftest_jit_source": (_ci, [_vp, _vp, _u64, C.POINTER(_u64)]),
     "sped_selftest_jit_compile": (_ci, [_vp, _ci, _ci, C.POINTER(_u64)]),
+}
+# test-only library (host emulation of the kernels, csrc/emul.cpp): not part of the product
+EMUL_LIB_PATH = os.path.join(_HERE, "lib", "libsped_emul.so")
+EMUL_SIGNATURES = {
     "sped_selftest_emulate_matvec": (_ci, [_vp, _u64, _vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, C.c_uint, _vp]),
 }
+_emul_lib = None
+
+
+def emulLib():
+    """libsped_emul.so: the kernels' device sources compiled by the host compiler (tests only)."""
+    global _emul_lib
+    if _emul_lib is None:
+        lib()
+        L = C.CDLL(EMUL_LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in EMUL_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _emul_lib = L
+    return _emul_lib
 
 
 def lib():

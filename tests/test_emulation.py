@@ -13,8 +13,6 @@ import pytest
 from helpers import SMALL_DECKS, extra_configs, oracle_problem, product_problem, splitmix_vector
 from spin_ed_b200 import decks, ffi
 
-WINDOW = os.environ.get("SPED_WINDOW", "1") != "0"  # class 0 = window class (shared-memory window of x)
-
 ONE_ROUND = os.environ.get("SPED_REMOTE_GROUPS", "") == "1"  # one exchange round (all-gather) even for > 2 ranks
 
 NAMES = SMALL_DECKS + ["chain_12_full_sym", "chain_12_pi", "chain_8_k1_complex", "chain_9_k2_nohw", "chain_10_inv_only",
@@ -28,8 +26,8 @@ def _emulate(op, reps, stab, world, rank, x, ncols=1):
     dt = x.dtype
     outs = [np.full(max(n_local, 1), 7.0, dtype=dt) for _ in range(3)]
     block = np.full((max(n_local, 1), max(ncols, 1)), 7.0, dtype=dt, order="F")
-    stats = (C.c_uint64 * 5)()
-    ffi.checkStatus(ffi.lib().sped_selftest_emulate_matvec(
+    stats = (C.c_uint64 * 4)()
+    ffi.checkStatus(ffi.emulLib().sped_selftest_emulate_matvec(
         op._ptr, n, reps.ctypes.data, stab.ctypes.data, world, rank, ffi.DTYPE_TAGS[np.dtype(dt)], x.ctypes.data,
         outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, stats, ncols, block.ctypes.data))
     rows = rd.local_rows().astype(np.int64)
@@ -57,21 +55,19 @@ def test_emulated_kernels_match_oracle(oracle, name):
     scale = np.linalg.norm(want)
     total = oop.count_offdiag()
     for world in (1, 2, 3, 4, 8):
-        elements = windowed = 0
+        elements = 0
         for rank in range(world):
             rows, (free, allc, phased), stats = _emulate(op, reps, stab, world, rank, x)
             elements += stats[1]
             rounds = 0 if world == 1 else 1 if (world == 2 or ONE_ROUND) else 2
-            assert stats[3] == 1 + (1 if WINDOW else 0) + rounds
-            assert stats[0] >= stats[1] >= stats[2] and stats[1] >= stats[4]
-            windowed += stats[4]
+            assert stats[3] == 1 + rounds
+            assert stats[0] >= stats[1] >= stats[2]
             for what, got in (("matrix-free", free), ("cached, one pass", allc), ("cached, class by class", phased)):
                 err = np.linalg.norm(got - want[rows])
                 assert err <= 1e-12 * scale, (name, world, rank, what, err / scale)
             # the one-pass and the class-by-class streaming results are the same sums in the same order
             assert np.array_equal(allc, phased), (name, world, rank)
         assert elements == total, (name, world, elements, total)
-        assert (windowed > 0) == (WINDOW and total > 0), (name, world, windowed)
     # block kernel (interleaved columns): 2, 3 and 4 columns, one and several ranks
     for ncols in (2, 3, 4):
         xb = np.asfortranarray(np.stack([np.roll(x, -c) for c in range(ncols)], axis=1))

@@ -26,6 +26,9 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert declared == set(ffi.SIGNATURES), declared ^ set(ffi.SIGNATURES)
+    # the host emulation of the kernels is a test-only library, not part of the product
+    assert not hasattr(L, "sped_selftest_emulate_matvec")
+    assert hasattr(C.CDLL(ffi.EMUL_LIB_PATH), "sped_selftest_emulate_matvec")
 
 
 def test_symmetry_semantics_of_reference_spec():
