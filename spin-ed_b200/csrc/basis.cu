@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "device_common.cuh"
@@ -353,9 +354,21 @@ void Basis::build() {
   d_binom.upload(host_binom.c, 65 * 65);
   EnumParams ep{0, total, hamming_weight, (int)n_spins, d_binom.ptr};
 
+  // a failed (re)build must not leave a half-initialised basis marked as built
+  built = false;
+  index = BasisIndex{};
   d_reps.release();
   d_stab.release();
   host_reps.reset();
+  // Sharding the enumeration over the ranks pays only for large sectors: below ~3e10 candidates one
+  // GPU walks the sector in well under a second, less than the exchange of the survivors costs
+  // (6x6, 9.1e9 candidates: 0.2 s on one GPU, 0.6-1.4 s sharded over 2-8).  Smaller sectors are
+  // enumerated redundantly by every rank -- no communication at all.  The choice depends on the
+  // sector and the environment only, so every rank makes the same one.
+  u64 shard_min = 1ull << 35;
+  if (char const* e = std::getenv("SPED_BUILD_SHARD_MIN")) shard_min = std::strtoull(e, nullptr, 10);
+  bool const sharded = cm.active() && total >= shard_min;
+  int const b_world = sharded ? cm.world : 1, b_rank = sharded ? cm.rank : 0;
   if (trivial()) {
     if (hamming_weight >= 0) {
       d_reps.alloc(total);
@@ -376,7 +389,7 @@ void Basis::build() {
     d_reps.alloc(std::max<u64>(expected, 1));
     // tiles of candidate ranks, interleaved over ranks
     u64 tile = 1ull << 30;
-    u64 want_tiles = (u64)cm.world * 8;
+    u64 want_tiles = (u64)b_world * 8;
     while (tile > kCandPerBlock * 16 && (total + tile - 1) / tile < want_tiles) tile >>= 1;
     u64 n_tiles = (total + tile - 1) / tile;
     u64 blocks_per_tile = (tile + kCandPerBlock - 1) / kCandPerBlock;
@@ -389,7 +402,7 @@ void Basis::build() {
     CUDA_CHECK(cudaMemset(d_flag.ptr, 0, sizeof(int)));
     DeviceBuffer<u64> d_staging;
     u64* out = d_reps.ptr;
-    if (cm.active()) {
+    if (sharded) {
       d_staging.alloc(std::max<u64>(expected, 1));
       out = d_staging.ptr;
     }
@@ -402,7 +415,7 @@ void Basis::build() {
       else CUDA_CHECK(cudaFuncSetAttribute(mark_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     for (u64 t = 0; t < n_tiles; ++t) {
-      if ((int)(t % (u64)cm.world) != cm.rank) continue;
+      if ((int)(t % (u64)b_world) != b_rank) continue;
       EnumParams e = ep;
       e.rank_lo = t * tile;
       e.rank_hi = std::min(total, (t + 1) * tile);
@@ -419,7 +432,7 @@ void Basis::build() {
     CUDA_CHECK(cudaDeviceSynchronize());
     int overflow = 0;
     CUDA_CHECK(cudaMemcpy(&overflow, d_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
-    if (cm.active()) {
+    if (sharded) {
       // every rank learns every tile's count, then each tile is broadcast from its owner into place
       comm_allreduce_sum_u64(reinterpret_cast<unsigned long long*>(d_scalars.ptr + 2), n_tiles, cm.stream);
       CUDA_CHECK(cudaStreamSynchronize(cm.stream));
@@ -470,6 +483,8 @@ void Basis::adopt(u64 size, u64 const* reps_in) {
   std::lock_guard<std::mutex> lock(mutex);
   ensure_device_tables();
   auto t0 = std::chrono::steady_clock::now();
+  built = false;  // a failing ls_build_unsafe must not leave the previous basis marked as built
+  index = BasisIndex{};
   host_reps.reset();
   d_stab.release();
   if (trivial() && hamming_weight < 0) {

@@ -237,6 +237,130 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(T const* V, T const*
   block_reduce_store(nrm, partial + blockIdx.x);
 }
 
+// ---- block forms: several vectors per pass, so that the basis V is read once for all of them ----
+// A kernel with a `gate` returns at once when *gate == 0: the second (DGKS) sweep of the block
+// orthogonalisation is queued unconditionally and decides on the device whether it has work.
+
+// partial[(j * NW + c) * gridDim.x + block] = sum_rows conj(V_j) w_c,  j < m, c < NW
+template <class T, int NW>
+__global__ void __launch_bounds__(kThreads) block_dot_kernel(T const* V, u64 ld, int m, T const* W, u64 ldw, u64 n,
+                                                             double2* partial, int const* gate) {
+  using A = typename VT<T>::Acc;
+  if (gate && *gate == 0) return;
+  constexpr int JC = NW == 1 ? 8 : (NW == 2 ? 6 : 4);
+  for (int j0 = 0; j0 < m; j0 += JC) {
+    double2 acc[JC][NW];
+#pragma unroll
+    for (int j = 0; j < JC; ++j)
+#pragma unroll
+      for (int c = 0; c < NW; ++c) acc[j][c] = make_double2(0, 0);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+      A wv[NW];
+#pragma unroll
+      for (int c = 0; c < NW; ++c) wv[c] = VT<T>::load(W + (u64)c * ldw + i);
+#pragma unroll
+      for (int j = 0; j < JC; ++j)
+        if (j0 + j < m) {
+          A const vv = VT<T>::load(V + (u64)(j0 + j) * ld + i);
+#pragma unroll
+          for (int c = 0; c < NW; ++c) dot_acc(acc[j][c], vv, wv[c]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < JC; ++j)
+      if (j0 + j < m) {
+#pragma unroll
+        for (int c = 0; c < NW; ++c) block_reduce_store(acc[j][c], partial + (u64)((j0 + j) * NW + c) * gridDim.x + blockIdx.x);
+      }
+  }
+}
+
+// w_c -= sum_j coeff[j * NW + c] V_j,  c < NW
+template <class T, int NW>
+__global__ void __launch_bounds__(kThreads) block_axpy_kernel(T const* V, u64 ld, int m, double2 const* coeff, T* W, u64 ldw,
+                                                              u64 n, int const* gate) {
+  using A = typename VT<T>::Acc;
+  if (gate && *gate == 0) return;
+  __shared__ double2 c[kMaxBasis * NW];
+  for (int j = threadIdx.x; j < m * NW; j += blockDim.x) c[j] = coeff[j];
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    A acc[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q) acc[q] = VT<T>::load(W + (u64)q * ldw + i);
+    for (int j = 0; j < m; ++j) {
+      A const vv = VT<T>::load(V + (u64)j * ld + i);
+#pragma unroll
+      for (int q = 0; q < NW; ++q) acc[q] = subv(acc[q], mulc(vv, c[j * NW + q]));
+    }
+#pragma unroll
+    for (int q = 0; q < NW; ++q) VT<T>::store(W + (u64)q * ldw + i, acc[q]);
+  }
+}
+
+// w *= 1 / sqrt(norm2[0].x), or 0 when the squared norm is not above `tiny` (a direction that is
+// linearly dependent on the basis becomes the zero vector, harmless for every later kernel; the
+// host replaces it when it reads the recorded norm).  record[0] = norm2; with `flag` given,
+// *flag is set when less than half of the (unit) input survived -- the DGKS criterion for a
+// second orthogonalisation sweep.
+template <class T>
+__global__ void __launch_bounds__(kThreads) scale_kernel(T* w, u64 n, double2 const* norm2, double tiny, double* record, int* flag,
+                                                         int const* gate) {
+  using A = typename VT<T>::Acc;
+  if (gate && *gate == 0) return;
+  double const v = norm2[0].x;
+  double const s = v > tiny ? rsqrt(v) : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (record) *record = v;
+    if (flag && v < 0.5) *flag = 1;
+  }
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    VT<T>::store(w + i, mulc(VT<T>::load(w + i), make_double2(s, 0)));
+}
+
+// out_q = sum_j (W_j - theta_q V_j) s[j * KQ + q] for q < KQ in ONE pass over V and W;
+// partial[q * gridDim.x + block] = sum |out_q|^2
+template <class T, int KQ>
+__global__ void __launch_bounds__(kThreads) residual_block_kernel(T const* V, T const* Wm, u64 ld, int m, double2 const* s,
+                                                                  double const* theta, T* out, u64 ldo, u64 n, double2* partial) {
+  using A = typename VT<T>::Acc;
+  __shared__ double2 c[kMaxBasis * KQ];
+  __shared__ double th[KQ];
+  for (int j = threadIdx.x; j < m * KQ; j += blockDim.x) c[j] = s[j];
+  if (threadIdx.x < KQ) th[threadIdx.x] = theta[threadIdx.x];
+  __syncthreads();
+  double2 nrm[KQ];
+#pragma unroll
+  for (int q = 0; q < KQ; ++q) nrm[q] = make_double2(0, 0);
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    A acc[KQ];
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) acc[q] = from2<A>(make_double2(0, 0));
+    for (int j = 0; j < m; ++j) {
+      A const wv = VT<T>::load(Wm + (u64)j * ld + i);
+      A const vv = VT<T>::load(V + (u64)j * ld + i);
+#pragma unroll
+      for (int q = 0; q < KQ; ++q) acc[q] = addv(acc[q], mulc(subv(wv, mulc(vv, make_double2(th[q], 0))), c[j * KQ + q]));
+    }
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      VT<T>::store(out + (u64)q * ldo + i, acc[q]);
+      dot_acc(nrm[q], acc[q], acc[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KQ; ++q) block_reduce_store(nrm[q], partial + (u64)q * gridDim.x + blockIdx.x);
+}
+
+// dst_q = src_q * scale[q]  (new search directions: residuals scaled to unit length)
+template <class T>
+__global__ void __launch_bounds__(kThreads) copy_scaled_kernel(T const* src, u64 lds, T* dst, u64 ldd, u64 n, double scale) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    VT<T>::store(dst + i, mulc(VT<T>::load(src + i), make_double2(scale, 0)));
+  (void)lds;
+  (void)ldd;
+}
+
 // rows of V (n x m) <- rows * C (m x p), in place; C row-major in global memory
 template <class T>
 __global__ void __launch_bounds__(kThreads) row_transform_kernel(T* V, u64 ld, int m, int p, double2 const* C, u64 n) {
@@ -284,65 +408,150 @@ double now_seconds() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Device time per phase of the solve, measured with CUDA events recorded on the solver's stream and
+// resolved once at the end (no host synchronisation inside the iteration for the sake of timing).
+struct PhaseTimer {
+  enum Phase { kMatvec, kOrtho, kResidual, kRestart, kProject, kOther, kPhases };
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  std::vector<int> phase_of;  // phase that ENDS at event i
+  size_t used = 0;
+  void start(cudaStream_t s) {
+    stream = s;
+    used = 0;
+    phase_of.clear();
+    mark(kOther);
+  }
+  void mark(int phase) {
+    if (used == events.size()) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      events.push_back(e);
+    }
+    CUDA_CHECK(cudaEventRecord(events[used++], stream));
+    phase_of.push_back(phase);
+  }
+  void resolve(double* seconds /* [kPhases] */) {
+    CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (size_t i = 1; i < used; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, events[i - 1], events[i]);
+      seconds[phase_of[i]] += ms * 1e-3;
+    }
+  }
+  ~PhaseTimer() {
+    for (auto e : events) cudaEventDestroy(e);
+  }
+};
+
 template <class T>
 struct Solver {
   Operator& op;
   int dtype;
-  u64 n_global, row0, n;  // local rows [row0, row0 + n)
-  u64 ld;                 // leading dimension of V and W (elements)
+  u64 n_global, n;        // global rows, rows of this rank
+  u64 ld;                 // leading dimension of V, W and the residual block (elements)
   int grid;
   cudaStream_t stream;
-  DeviceBuffer<T> V, Wm, xfull;
-  DeviceBuffer<double2> partial, scal, coeff;
+  // views into the operator's grow-only workspace (see Operator::workspace)
+  template <class U>
+  struct Ws {
+    U* ptr = nullptr;
+    size_t count = 0;
+    void take(Operator& o, int slot, size_t n) {
+      ptr = static_cast<U*>(o.workspace(slot, std::max<size_t>(n, 1) * sizeof(U)));
+      count = n;
+    }
+  };
+  Ws<T> V, Wm, xfull, resid;
+  Ws<double2> partial, scal, coeff, transform_coeff;
+  Ws<double> d_theta, d_norms;
+  Ws<int> d_flag;
   u64 chunk;              // rows per rank in the replicated vector
   EighStats stats;
+  PhaseTimer timer;
+  static constexpr int kGroup = 4;  // vectors handled together by the block kernels
 
   Solver(Operator& o, int dt) : op(o), dtype(dt) {}
 
   void sync() { CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
-  // out_host[j] = <V_j, w> for j < ncols (all-reduced)
-  std::vector<cplx> dots(T const* Vp, int ncols, T const* w, bool to_host, double2* dev_out = nullptr) {
-    double2* out = dev_out ? dev_out : scal.ptr;
-    multi_dot_kernel<T><<<grid, kThreads, 0, stream>>>(Vp, ld, ncols, w, n, partial.ptr);
-    KERNEL_LAUNCHED();
-    finish_dot_kernel<<<(ncols + 63) / 64, 64, 0, stream>>>(partial.ptr, grid, ncols, out);
-    KERNEL_LAUNCHED();
-    comm_allreduce_sum_f64(reinterpret_cast<double*>(out), 2 * (size_t)ncols, stream);
-    std::vector<cplx> h;
-    if (to_host) {
-      std::vector<double2> tmp(ncols);
-      CUDA_CHECK(cudaMemcpyAsync(tmp.data(), out, sizeof(double2) * ncols, cudaMemcpyDeviceToHost, stream));
-      sync();
-      h.resize(ncols);
-      for (int j = 0; j < ncols; ++j) h[j] = cplx(tmp[j].x, tmp[j].y);
+  // ---- launches (all asynchronous on `stream`) ----
+  // out[j * nw + c] = <V_j, w_c>, all-reduced, left on the device
+  void block_dots(T const* Vp, int m, T const* W, int nw, double2* out, int const* gate = nullptr) {
+    switch (nw) {
+      case 1: block_dot_kernel<T, 1><<<grid, kThreads, 0, stream>>>(Vp, ld, m, W, ld, n, partial.ptr, gate); break;
+      case 2: block_dot_kernel<T, 2><<<grid, kThreads, 0, stream>>>(Vp, ld, m, W, ld, n, partial.ptr, gate); break;
+      case 3: block_dot_kernel<T, 3><<<grid, kThreads, 0, stream>>>(Vp, ld, m, W, ld, n, partial.ptr, gate); break;
+      default: block_dot_kernel<T, 4><<<grid, kThreads, 0, stream>>>(Vp, ld, m, W, ld, n, partial.ptr, gate); break;
     }
+    KERNEL_LAUNCHED();
+    finish_dot_kernel<<<(m * nw + 63) / 64, 64, 0, stream>>>(partial.ptr, grid, m * nw, out);
+    KERNEL_LAUNCHED();
+    comm_allreduce_sum_f64(reinterpret_cast<double*>(out), 2 * (size_t)m * nw, stream);
+  }
+  void block_axpy(T const* Vp, int m, double2 const* c, T* W, int nw, int const* gate = nullptr) {
+    switch (nw) {
+      case 1: block_axpy_kernel<T, 1><<<grid, kThreads, 0, stream>>>(Vp, ld, m, c, W, ld, n, gate); break;
+      case 2: block_axpy_kernel<T, 2><<<grid, kThreads, 0, stream>>>(Vp, ld, m, c, W, ld, n, gate); break;
+      case 3: block_axpy_kernel<T, 3><<<grid, kThreads, 0, stream>>>(Vp, ld, m, c, W, ld, n, gate); break;
+      default: block_axpy_kernel<T, 4><<<grid, kThreads, 0, stream>>>(Vp, ld, m, c, W, ld, n, gate); break;
+    }
+    KERNEL_LAUNCHED();
+  }
+  std::vector<cplx> to_host(double2 const* dev, int count) {
+    std::vector<double2> tmp(count);
+    CUDA_CHECK(cudaMemcpyAsync(tmp.data(), dev, sizeof(double2) * count, cudaMemcpyDeviceToHost, stream));
+    sync();
+    std::vector<cplx> h(count);
+    for (int j = 0; j < count; ++j) h[j] = cplx(tmp[j].x, tmp[j].y);
     return h;
   }
 
-  // w <- (I - V V^H) w, then normalise; returns the norm after projection.  Classical
-  // Gram-Schmidt with the DGKS criterion: a unit-length w that keeps more than half of its squared
-  // norm after the first projection needs no second pass (residuals of Ritz pairs are orthogonal to
-  // the basis up to round-off, so this is the common case and saves a full sweep over V).
-  double orthonormalize(int m, T* w, bool unit_norm_input = false) {
-    double t0 = now_seconds();
-    for (int pass = 0; pass < 2 && m > 0; ++pass) {
-      auto c = dots(V.ptr, m, w, unit_norm_input, coeff.ptr);
-      multi_axpy_kernel<T><<<grid, kThreads, 0, stream>>>(V.ptr, ld, m, coeff.ptr, w, n);
+  // One sweep of the block orthogonalisation of W[:, 0:nw) (unit-length columns on entry of the
+  // first sweep): against V[:, 0:m) -- V read once for the whole group -- then column by column
+  // inside the group; every column ends normalised, its squared norm BEFORE the scaling recorded
+  // in norms_out[c].  first sweep: `raise` is set when some column kept less than half of its
+  // length (DGKS: a second sweep is due); second sweep: every kernel is gated on that flag.
+  void ortho_sweep(int m, T* W, int nw, double* norms_out, int* raise, int const* gate) {
+    if (m > 0) {
+      block_dots(V.ptr, m, W, nw, coeff.ptr, gate);
+      block_axpy(V.ptr, m, coeff.ptr, W, nw, gate);
+    }
+    for (int c = 0; c < nw; ++c) {
+      T* wc = W + (u64)c * ld;
+      block_dots(wc, 1, wc, 1, scal.ptr, gate);
+      scale_kernel<T><<<grid, kThreads, 0, stream>>>(wc, n, scal.ptr, 1e-24, norms_out ? norms_out + c : nullptr, raise, gate);
       KERNEL_LAUNCHED();
-      if (unit_norm_input) {
-        double removed = 0;
-        for (auto const& v : c) removed += std::norm(v);
-        if (removed < 0.5) break;
+      if (c + 1 < nw) {
+        block_dots(wc, 1, wc + ld, nw - 1 - c, coeff.ptr, gate);
+        block_axpy(wc, 1, coeff.ptr, wc + ld, nw - 1 - c, gate);
       }
     }
-    auto nn = dots(w, 1, w, true);
-    double nrm = std::sqrt(std::max(0.0, nn[0].real()));
+  }
+
+  // New search directions W[:, 0:nw) (columns of V past the first m), unit length on entry:
+  // classical Gram-Schmidt by blocks with the DGKS criterion, entirely on the device.  The squared
+  // norms that decide whether a direction broke down (linearly dependent on the basis) are left
+  // in d_norms[slot .. slot + nw) for the host to read with the next round trip.
+  void ortho_block(int m, T* W, int nw, int slot) {
+    CUDA_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(int), stream));
+    ortho_sweep(m, W, nw, d_norms.ptr + slot, d_flag.ptr, nullptr);
+    ortho_sweep(m, W, nw, nullptr, nullptr, d_flag.ptr);
+  }
+
+  // sequential, host-synchronous form (start vectors and replacements of broken-down directions)
+  double orthonormalize(int m, T* w) {
+    for (int pass = 0; pass < 2 && m > 0; ++pass) {
+      block_dots(V.ptr, m, w, 1, coeff.ptr);
+      block_axpy(V.ptr, m, coeff.ptr, w, 1);
+    }
+    block_dots(w, 1, w, 1, scal.ptr);
+    double const nn = to_host(scal.ptr, 1)[0].real();
+    double const nrm = std::sqrt(std::max(0.0, nn));
     if (nrm > 0) {
-      normalize_kernel<T><<<grid, kThreads, 0, stream>>>(w, n, scal.ptr);
+      scale_kernel<T><<<grid, kThreads, 0, stream>>>(w, n, scal.ptr, 0.0, nullptr, nullptr, nullptr);
       KERNEL_LAUNCHED();
     }
-    stats.seconds_ortho += now_seconds() - t0;
     return nrm;
   }
 
@@ -351,36 +560,31 @@ struct Solver {
     KERNEL_LAUNCHED();
   }
 
-  // Wm[:, j0:j0+nb] = H V[:, j0:j0+nb]
+  // Wm[:, j0:j0+nb] = H V[:, j0:j0+nb]   (asynchronous)
   void apply(int j0, int nb) {
-    double t0 = now_seconds();
     Comm& cm = comm();
     if (!cm.active()) {
       op.matmat_device(dtype, nb, V.ptr + (u64)j0 * ld, ld, Wm.ptr + (u64)j0 * ld, ld, stream);
     } else {
-      // per column: all-gather of the shard overlapped with the local-source pass (operator.cu)
+      // per column: exchange of the shards overlapped with the passes over the source classes (operator.cu)
       for (int c = 0; c < nb; ++c)
         op.matvec_sharded(dtype, V.ptr + (u64)(j0 + c) * ld, Wm.ptr + (u64)(j0 + c) * ld, xfull.ptr, stream);
     }
-    sync();
     stats.matvecs += nb;
-    stats.seconds_matvec += now_seconds() - t0;
+    timer.mark(PhaseTimer::kMatvec);
   }
 
   void transform(T* M, int m, int p, std::vector<cplx> const& C) {
     std::vector<double2> c((size_t)m * p);
     for (size_t i = 0; i < c.size(); ++i) c[i] = make_double2(C[i].real(), C[i].imag());
-    if (transform_coeff.count < c.size()) transform_coeff.alloc((size_t)kMaxBasis * kMaxBasis);
+    // (pageable source: the call returns once the data is staged, so `c` may go out of scope)
     CUDA_CHECK(cudaMemcpyAsync(transform_coeff.ptr, c.data(), c.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     size_t smem = c.size() * sizeof(double2);
     if (smem > 48 * 1024)
       CUDA_CHECK(cudaFuncSetAttribute(row_transform_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     row_transform_kernel<T><<<grid, kThreads, smem, stream>>>(M, ld, m, p, transform_coeff.ptr, n);
     KERNEL_LAUNCHED();
-    sync();  // `c` is pageable host memory read by the async copy
   }
-  DeviceBuffer<double2> transform_coeff;
-
   int run(u64 k, double eps, int m_max, int b_max, int m_min, double* evals_out, void* evecs_out, double* rnorms_out,
           sped_monitor_fn monitor, void* mctx) {
     double t_start = now_seconds();
@@ -388,16 +592,18 @@ struct Solver {
     Comm& cm = comm();
     n_global = B.n_states;
     op.prepare();
-    row0 = 0;
     n = op.dist.n_local;
     chunk = op.dist.chunk;
     if (k == 0 || k > n_global) fail(LS_INVALID_ARGUMENT, "number of eigenpairs must be in 1..dimension");
-    // option defaults
+    // option defaults (PRIMME's meaning of the three sizes); everything is kept within kMaxBasis
     int b = b_max > 0 ? b_max : (int)std::min<u64>(k, 8);
-    b = (int)std::min<u64>((u64)b, n_global);
+    b = (int)std::min<u64>((u64)std::min(b, kMaxBasis / 2), n_global);
     int mmax = m_max > 0 ? m_max : std::max<int>(4 * b + 2 * (int)k, 24);
     mmax = (int)std::min<u64>((u64)std::min(mmax, kMaxBasis), n_global);
     if (mmax < (int)k + 1 && (u64)mmax < n_global) mmax = (int)std::min<u64>(n_global, k + 1 + (u64)b);
+    mmax = std::min(mmax, kMaxBasis);
+    if (mmax < (int)k && (u64)mmax < n_global)
+      fail(LS_INVALID_ARGUMENT, "max_primme_basis_size is too small for the number of eigenpairs");
     if (b > mmax) b = mmax;
     int keep = m_min > 0 ? m_min : std::max<int>((int)k, mmax / 3);
     double const mach = (dtype == SPED_F32 || dtype == SPED_C64) ? 1.1920928955078125e-07 : 2.220446049250313e-16;
@@ -406,43 +612,62 @@ struct Solver {
     stream = cm.active() ? cm.stream : nullptr;
     ld = std::max<u64>(n, 1);
     grid = persistent_grid(std::max<u64>(n, 1), kThreads, 4);
-    V.alloc(ld * mmax);
-    Wm.alloc(ld * mmax);
-    if (cm.active()) xfull.alloc(chunk * cm.world);
-    partial.alloc((size_t)grid * kMaxBasis);
-    scal.alloc(kMaxBasis);
-    coeff.alloc(kMaxBasis);
+    int const kcap = (int)std::min<u64>(k, (u64)kMaxBasis);
+    V.take(op, 0, ld * mmax);
+    Wm.take(op, 1, ld * mmax);
+    resid.take(op, 2, ld * std::max(1, kcap));
+    if (cm.active()) xfull.take(op, 3, chunk * cm.world);
+    partial.take(op, 4, (size_t)grid * kMaxBasis * kGroup);
+    scal.take(op, 5, kMaxBasis);
+    coeff.take(op, 6, (size_t)kMaxBasis * kMaxBasis);
+    d_theta.take(op, 7, kMaxBasis);
+    d_norms.take(op, 8, kMaxBasis);
+    d_flag.take(op, 9, 1);
+    transform_coeff.take(op, 10, (size_t)kMaxBasis * kMaxBasis);
     if (cm.active()) CUDA_CHECK(cudaMemsetAsync(xfull.ptr, 0, chunk * cm.world * sizeof(T), stream));
+    timer.start(stream);
 
     std::vector<cplx> H((size_t)mmax * mmax, cplx(0, 0));  // projected matrix, row-major, leading dim mmax
     auto Hat = [&](int i, int j) -> cplx& { return H[(size_t)i * mmax + j]; };
     int m = 0;
     u64 seed = 0x5EED0002ull;
-    auto append_random = [&]() {
+    auto append_random = [&](int at) {
       for (int attempt = 0; attempt < 8; ++attempt) {
-        randomize(V.ptr + (u64)m * ld, seed);
+        randomize(V.ptr + (u64)at * ld, seed);
         seed += 0x1000193ull;
-        if (orthonormalize(m, V.ptr + (u64)m * ld) > 1e-8) return;
+        if (orthonormalize(at, V.ptr + (u64)at * ld) > 1e-8) return;
       }
       fail(SPED_INTERNAL_ERROR, "could not generate a new search direction");
     };
+    // H[:, m_old:m_new) = V[:, 0:m_new)^H W[:, m_old:m_new), groups of kGroup columns per pass over V;
+    // one device-to-host round trip for the whole block
     auto extend_projection = [&](int m_old, int m_new) {
-      double t_pr = now_seconds();
-      for (int j = m_old; j < m_new; ++j) {
-        auto h = dots(V.ptr, m_new, Wm.ptr + (u64)j * ld, true);
-        for (int i = 0; i < m_new; ++i) {
-          Hat(i, j) = h[i];
-          Hat(j, i) = std::conj(h[i]);
-        }
-        Hat(j, j) = Hat(j, j).real();
+      int off = 0;
+      for (int j0 = m_old; j0 < m_new; j0 += kGroup) {
+        int const nw = std::min(kGroup, m_new - j0);
+        block_dots(V.ptr, m_new, Wm.ptr + (u64)j0 * ld, nw, coeff.ptr + off);
+        off += m_new * nw;
       }
-      stats.seconds_project += now_seconds() - t_pr;
+      auto h = to_host(coeff.ptr, off);
+      off = 0;
+      for (int j0 = m_old; j0 < m_new; j0 += kGroup) {
+        int const nw = std::min(kGroup, m_new - j0);
+        for (int i = 0; i < m_new; ++i)
+          for (int c = 0; c < nw; ++c) {
+            Hat(i, j0 + c) = h[off + i * nw + c];
+            Hat(j0 + c, i) = std::conj(h[off + i * nw + c]);
+          }
+        off += m_new * nw;
+      }
+      for (int j = m_old; j < m_new; ++j) Hat(j, j) = Hat(j, j).real();
+      timer.mark(PhaseTimer::kProject);
     };
     int const b0 = std::min<int>(mmax, std::max<int>(b, (int)std::min<u64>(k, (u64)mmax)));
     for (int j = 0; j < b0; ++j) {
-      append_random();
+      append_random(m);
       ++m;
     }
+    timer.mark(PhaseTimer::kOrtho);
     apply(0, m);
     extend_projection(0, m);
 
@@ -461,31 +686,48 @@ struct Solver {
       small_eigh(m, Hm, theta, S);
       for (double t : theta) a_norm = std::max(a_norm, std::abs(t));
       int const kk = (int)std::min<u64>(k, (u64)m);
-      // residuals of the wanted pairs; the first `b` unconverged ones become new directions,
-      // written straight into the free columns of V when there is room, otherwise after a restart
+      // residuals of ALL wanted pairs, kGroup per pass over V and W, one round trip for their norms
+      bool const have_all = m >= (int)k;
+      {
+        std::vector<double2> sblock;
+        std::vector<double> th;
+        int off = 0;
+        for (int q0 = 0; q0 < kk; q0 += kGroup) {
+          int const kq = std::min(kGroup, kk - q0);
+          sblock.assign((size_t)m * kq, make_double2(0, 0));
+          th.assign(kq, 0.0);
+          for (int q = 0; q < kq; ++q) {
+            th[q] = theta[q0 + q];
+            for (int j = 0; j < m; ++j) sblock[(size_t)j * kq + q] = make_double2(S[(size_t)j * m + q0 + q].real(), S[(size_t)j * m + q0 + q].imag());
+          }
+          CUDA_CHECK(cudaMemcpyAsync(coeff.ptr, sblock.data(), sizeof(double2) * sblock.size(), cudaMemcpyHostToDevice, stream));
+          CUDA_CHECK(cudaMemcpyAsync(d_theta.ptr, th.data(), sizeof(double) * kq, cudaMemcpyHostToDevice, stream));
+          T* out = resid.ptr + (u64)q0 * ld;
+          switch (kq) {
+            case 1: residual_block_kernel<T, 1><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
+            case 2: residual_block_kernel<T, 2><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
+            case 3: residual_block_kernel<T, 3><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
+            default: residual_block_kernel<T, 4><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
+          }
+          KERNEL_LAUNCHED();
+          finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, kq, scal.ptr + off);
+          KERNEL_LAUNCHED();
+          off += kq;
+        }
+        comm_allreduce_sum_f64(reinterpret_cast<double*>(scal.ptr), 2 * (size_t)kk, stream);
+        auto r2 = to_host(scal.ptr, kk);
+        for (int i = 0; i < kk; ++i) {
+          rn[i] = std::sqrt(std::max(0.0, r2[i].real()));
+          ev[i] = theta[i];
+        }
+        timer.mark(PhaseTimer::kResidual);
+      }
       std::vector<int> unconverged;
       int n_conv = 0;
-      bool have_all = m >= (int)k;
-      double t_res = now_seconds();
       for (int i = 0; i < kk; ++i) {
-        std::vector<double2> s(m);
-        for (int j = 0; j < m; ++j) s[j] = make_double2(S[(size_t)j * m + i].real(), S[(size_t)j * m + i].imag());
-        CUDA_CHECK(cudaMemcpyAsync(coeff.ptr, s.data(), sizeof(double2) * m, cudaMemcpyHostToDevice, stream));
-        residual_kernel<T><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, theta[i], scratch(i), n,
-                                                          partial.ptr);
-        KERNEL_LAUNCHED();
-        finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, 1, scal.ptr);
-        KERNEL_LAUNCHED();
-        comm_allreduce_sum_f64(reinterpret_cast<double*>(scal.ptr), 2, stream);
-        double2 r2;
-        CUDA_CHECK(cudaMemcpyAsync(&r2, scal.ptr, sizeof(double2), cudaMemcpyDeviceToHost, stream));
-        sync();
-        rn[i] = std::sqrt(std::max(0.0, r2.x));
-        ev[i] = theta[i];
         if (rn[i] <= tol * a_norm) ++n_conv;
         else unconverged.push_back(i);
       }
-      stats.seconds_residual += now_seconds() - t_res;
       if (monitor) {
         sped_eigh_info info{it, m, n_conv, (int)k, stats.matvecs, ev.data(), rn.data(), now_seconds() - t_start};
         if (monitor(&info, mctx) != 0) break;
@@ -504,7 +746,6 @@ struct Solver {
       nb = (int)std::min<u64>((u64)nb, n_global - (u64)m);
       // restart when the new directions do not fit
       if (m + nb > mmax) {
-        double t_rs = now_seconds();
         int r = std::min(std::max(keep, (int)std::min<u64>(k, (u64)m)), mmax - nb);
         r = std::max(r, 1);
         int p_room = mmax - nb - r;
@@ -535,7 +776,6 @@ struct Solver {
         std::vector<cplx> C((size_t)m * p);
         for (int q = 0; q < p; ++q)
           for (int j = 0; j < m; ++j) C[(size_t)j * p + q] = cols[q][j];
-        // move the pending residuals out of the way is unnecessary: scratch lives outside V
         transform(V.ptr, m, p, C);
         transform(Wm.ptr, m, p, C);
         std::vector<cplx> Hn((size_t)p * p, cplx(0, 0));
@@ -556,7 +796,7 @@ struct Solver {
         for (int q = 0; q < p; ++q) S[(size_t)q * p + q] = 1.0;
         m = p;
         ++stats.restarts;
-        stats.seconds_restart += now_seconds() - t_rs;
+        timer.mark(PhaseTimer::kRestart);
       }
       // remember the current Ritz directions (for the "+k" part of the next restart)
       n_prev = (int)std::min<u64>((u64)std::max(1, std::min(b, (int)k)), (u64)m);
@@ -564,26 +804,60 @@ struct Solver {
       S_prev.assign((size_t)m * n_prev, cplx(0, 0));
       for (int q = 0; q < n_prev; ++q)
         for (int j = 0; j < m; ++j) S_prev[(size_t)j * n_prev + q] = S[(size_t)j * m + q];
-      // expand
-      int m_old = m;
+      // expand: the first nb unconverged residuals, scaled to unit length, become columns m .. m+nb
+      // of V and are orthonormalised by blocks on the device; a direction without a usable residual
+      // (the basis is still smaller than the number of wanted pairs) is a random vector
+      int const m_old = m;
+      std::vector<int> random_cols;
       for (int q = 0; q < nb; ++q) {
-        T* dst = V.ptr + (u64)m * ld;
-        bool ok = false;
-        if (q < (int)unconverged.size()) {
-          CUDA_CHECK(cudaMemcpyAsync(dst, scratch(unconverged[q]), n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
-          // scale to unit length first so the breakdown test is relative
-          auto nn = dots(dst, 1, dst, true);
-          if (nn[0].real() > 0) {
-            normalize_kernel<T><<<grid, kThreads, 0, stream>>>(dst, n, scal.ptr);
-            KERNEL_LAUNCHED();
-            ok = orthonormalize(m, dst, true) > 1e-7;
-          }
+        T* dst = V.ptr + (u64)(m_old + q) * ld;
+        if (q < (int)unconverged.size() && rn[unconverged[q]] > 0) {
+          copy_scaled_kernel<T><<<grid, kThreads, 0, stream>>>(resid.ptr + (u64)unconverged[q] * ld, ld, dst, ld, n, 1.0 / rn[unconverged[q]]);
+          KERNEL_LAUNCHED();
+        } else {
+          random_cols.push_back(q);
         }
-        if (!ok) append_random();
-        ++m;
       }
-      apply(m_old, m - m_old);
+      if (!random_cols.empty()) {
+        // rare: place the residual-based directions first, then the random ones sequentially
+        std::vector<int> res_cols;
+        for (int q = 0; q < nb; ++q)
+          if (std::find(random_cols.begin(), random_cols.end(), q) == random_cols.end()) res_cols.push_back(q);
+        int at = m_old;
+        for (int q : res_cols) {
+          if (m_old + q != at)
+            CUDA_CHECK(cudaMemcpyAsync(V.ptr + (u64)at * ld, V.ptr + (u64)(m_old + q) * ld, n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+          ++at;
+        }
+        int const n_res = (int)res_cols.size();
+        for (int g0 = 0; g0 < n_res; g0 += kGroup)
+          ortho_block(m_old + g0, V.ptr + (u64)(m_old + g0) * ld, std::min(kGroup, n_res - g0), g0);
+        for (int q = n_res; q < nb; ++q) append_random(m_old + q);
+      } else {
+        for (int g0 = 0; g0 < nb; g0 += kGroup)
+          ortho_block(m_old + g0, V.ptr + (u64)(m_old + g0) * ld, std::min(kGroup, nb - g0), g0);
+      }
+      m = m_old + nb;
+      timer.mark(PhaseTimer::kOrtho);
+      apply(m_old, nb);
+      // breakdown check rides on the projection's round trip: norms recorded by the block sweeps
+      std::vector<double> kept(nb, 1.0);
+      int const n_checked = nb - (int)random_cols.size();
+      if (n_checked > 0)
+        CUDA_CHECK(cudaMemcpyAsync(kept.data(), d_norms.ptr, sizeof(double) * n_checked, cudaMemcpyDeviceToHost, stream));
       extend_projection(m_old, m);
+      bool redo = false;
+      for (int q = 0; q < n_checked; ++q)
+        if (!(kept[q] > 1e-24)) {  // linearly dependent direction (stored as zeros): replace it
+          append_random(m_old + q);
+          redo = true;
+        }
+      if (redo) {
+        timer.mark(PhaseTimer::kOrtho);
+        apply(m_old, nb);
+        stats.matvecs -= nb;  // counted once
+        extend_projection(m_old, m);
+      }
     }
 
     // Ritz vectors of the wanted pairs: V <- V S(:, 0:k)
@@ -599,13 +873,18 @@ struct Solver {
       transform(V.ptr, m, kk, C);
     }
     for (u64 i = 0; i < k; ++i) {
-      evals_out[i] = i < (u64)kk ? theta[i] : 0.0;
+      // eigenvalues and residual norms of the same (last evaluated) Ritz pairs
+      evals_out[i] = i < (u64)kk ? (status == LS_SUCCESS ? theta[i] : ev[i]) : 0.0;
       rnorms_out[i] = i < (u64)kk ? rn[i] : 0.0;
     }
     if (evecs_out) {
       T* host = static_cast<T*>(evecs_out);
       if (!cm.active()) {
-        CUDA_CHECK(cudaMemcpy2D(host, n_global * sizeof(T), V.ptr, ld * sizeof(T), n * sizeof(T), kk, cudaMemcpyDeviceToHost));
+        // column by column: a 2-D copy would need a pitch of n_global * sizeof(T) bytes, which CUDA
+        // limits to 2^31 - 1 (sectors above ~2.7e8 f64 rows)
+        for (int q = 0; q < kk; ++q)
+          CUDA_CHECK(cudaMemcpyAsync(host + (u64)q * n_global, V.ptr + (u64)q * ld, n * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        sync();
       } else {
         // all-gather gives the [rank][local] layout; the blocks are put back in global row order
         // on the host (one memcpy per block of 2^log2b rows)
@@ -625,15 +904,17 @@ struct Solver {
         }
       }
     }
+    timer.mark(PhaseTimer::kOther);
+    double phase[PhaseTimer::kPhases] = {0, 0, 0, 0, 0, 0};
+    timer.resolve(phase);
+    stats.seconds_matvec = phase[PhaseTimer::kMatvec];
+    stats.seconds_ortho = phase[PhaseTimer::kOrtho];
+    stats.seconds_residual = phase[PhaseTimer::kResidual];
+    stats.seconds_restart = phase[PhaseTimer::kRestart];
+    stats.seconds_project = phase[PhaseTimer::kProject];
     stats.seconds_total = now_seconds() - t_start;
     op.last_stats = stats;
     return status;
-  }
-
-  // residual scratch: k columns kept in a separate buffer
-  DeviceBuffer<T> scratch_buf;
-  T* scratch(int i) {
-    return scratch_buf.ptr + (u64)i * ld;
   }
 };
 
@@ -641,9 +922,6 @@ template <class T>
 int run_solver(Operator& op, int dtype, u64 k, double eps, int m_max, int b_max, int m_min, double* evals, void* evecs,
                double* rnorms, sped_monitor_fn monitor, void* ctx) {
   Solver<T> s(op, dtype);
-  op.prepare();
-  u64 n = op.dist.n_local;
-  s.scratch_buf.alloc(std::max<u64>(n, 1) * std::max<u64>(1, std::min<u64>(k, (u64)kMaxBasis)));
   return s.run(k, eps, m_max, b_max, m_min, evals, evecs, rnorms, monitor, ctx);
 }
 

@@ -209,6 +209,16 @@ struct Operator {
   DeviceBuffer<double> d_diag;          // local rows (real part) [+ imaginary part if !real_diagonal]
   DeviceBuffer<unsigned char> stage_x, stage_y;  // grow-only device staging of the host-pointer entry
   DeviceBuffer<unsigned char> block_x;           // grow-only: interleaved copy of a block of vectors (opcache.cu)
+  // grow-only device workspace of sped_eigh (Krylov basis, H V, residuals, ...), kept between calls:
+  // cudaFree of multi-gigabyte buffers costs 0.1-0.8 s of wall time, more than a warm 6x6 solve
+  DeviceBuffer<unsigned char> eigh_ws[12];
+  void* workspace(int slot, size_t bytes) {
+    if (eigh_ws[slot].count < bytes) eigh_ws[slot].alloc(bytes);
+    return eigh_ws[slot].ptr;
+  }
+  void release_workspace() {
+    for (auto& b : eigh_ws) b.release();
+  }
 
   // operator cache (opcache.cu): off-diagonal elements of the local rows resident in HBM
   int cache_mode = -1;        // -1: auto (build when it fits), 0: never, 1: always try

@@ -584,63 +584,87 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   Comm& cm = comm();
   u64 padded = dist.chunk * dist.world;
   // staging buffers are kept between calls (PRIMME calls this once per block per iteration)
+  if (cm.active()) {
+    // Several ranks (every rank is handed the full x and wants the full y): a rank uploads only the
+    // rows it owns -- its blocks of the block-cyclic distribution are a strided 2-D copy -- the shards
+    // are exchanged over NVLink inside the sharded matvec, the result shards are all-gathered, and
+    // the [rank][local] layout is put back into global row order by the copy engines on the way out
+    // (one strided 2-D copy per owner).  PCIe carries N/P entries in and N out per rank.
+    if (stage_y.count < 2 * padded * es) stage_y.alloc(2 * padded * es);
+    unsigned char* xp = stage_y.ptr;
+    unsigned char* yp = stage_y.ptr + padded * es;
+    cudaStream_t st = cm.stream;
+    u64 const B = (u64)1 << dist.log2b, full = size >> dist.log2b, rem = size & (B - 1);
+    auto blocks_of = [&](u32 r) { return full / dist.world + (r < full % dist.world ? 1 : 0); };
+    for (u64 c = 0; c < block; ++c) {
+      unsigned char const* xc = static_cast<unsigned char const*>(x) + c * xs * es;
+      unsigned char* yc = static_cast<unsigned char*>(y) + c * ys * es;
+      unsigned char* mine = xp + (u64)dist.rank * dist.chunk * es;
+      u64 const nb = blocks_of(dist.rank);
+      if (nb)
+        CUDA_CHECK(cudaMemcpy2DAsync(mine, B * es, xc + (u64)dist.rank * B * es, (u64)dist.world * B * es, B * es, nb,
+                                     cudaMemcpyHostToDevice, st));
+      if (rem && dist.rank == full % dist.world)
+        CUDA_CHECK(cudaMemcpyAsync(mine + nb * B * es, xc + full * B * es, rem * es, cudaMemcpyHostToDevice, st));
+      matvec_sharded(dtype, mine, yp + (u64)dist.rank * dist.chunk * es, xp, st);
+      comm_allgather_inplace(yp, dist.chunk * es, st);
+      for (u32 r = 0; r < dist.world; ++r) {
+        u64 const nbr = blocks_of(r);
+        unsigned char const* src = yp + (u64)r * dist.chunk * es;
+        if (nbr)
+          CUDA_CHECK(cudaMemcpy2DAsync(yc + (u64)r * B * es, (u64)dist.world * B * es, src, B * es, B * es, nbr,
+                                       cudaMemcpyDeviceToHost, st));
+        if (rem && r == full % dist.world)
+          CUDA_CHECK(cudaMemcpyAsync(yc + full * B * es, src + nbr * B * es, rem * es, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return;
+  }
   if (stage_x.count < size * block * es) stage_x.alloc(size * block * es);
-  size_t need_y = cm.active() ? 2 * padded * es : size * block * es;
-  if (stage_y.count < need_y) stage_y.alloc(need_y);
+  if (stage_y.count < size * block * es) stage_y.alloc(size * block * es);
   DeviceBuffer<unsigned char>&dx = stage_x, &dy = stage_y;
-  CUDA_CHECK(cudaMemcpy2D(dx.ptr, size * es, x, xs * es, size * es, block, cudaMemcpyHostToDevice));
-  // from pageable memory cudaMemcpy returns once the data is staged, possibly before the last DMA into
+  // column by column: a 2-D copy would need a pitch of xs * es bytes, which CUDA limits to 2^31 - 1
+  for (u64 c = 0; c < block; ++c)
+    CUDA_CHECK(cudaMemcpyAsync(dx.ptr + c * size * es, static_cast<unsigned char const*>(x) + c * xs * es, size * es,
+                               cudaMemcpyHostToDevice, nullptr));
+  // from pageable memory the copy returns once the data is staged, possibly before the last DMA into
   // dx has finished; the kernels below run on non-blocking streams, which the legacy stream does not
   // order -- so wait for it explicitly
   CUDA_CHECK(cudaStreamSynchronize(nullptr));
-  if (!cm.active()) {
-    constexpr int kPipe = 8;
-    u64 const rows_per = ((size + kPipe - 1) / kPipe + 31) & ~(u64)31;
-    if (cache_usable() && block == 1 && size >= (u64)1 << 20) {
-      // steady state: the streaming kernel runs row chunk by row chunk and the device-to-host copy
-      // of a finished chunk overlaps the kernel of the next one
-      if (!pipe_compute) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_copy, cudaStreamNonBlocking));
-        for (auto& e : pipe_events) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      }
-      // all kernels are queued first: a copy into pageable memory blocks the host, and must not
-      // keep the next chunk's kernel from being launched
-      int chunks = 0;
-      for (int c = 0; c < kPipe; ++c) {
-        u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
-        if (lo >= hi) break;
-        cached_matmat(dtype, 1, dx.ptr, size, dy.ptr, size, pipe_compute, lo, hi);
-        CUDA_CHECK(cudaEventRecord(pipe_events[c], pipe_compute));
-        chunks = c + 1;
-      }
-      for (int c = 0; c < chunks; ++c) {
-        u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
-        CUDA_CHECK(cudaStreamWaitEvent(pipe_copy, pipe_events[c], 0));
-        CUDA_CHECK(cudaMemcpyAsync(static_cast<unsigned char*>(y) + lo * es, dy.ptr + lo * es, (hi - lo) * es,
-                                   cudaMemcpyDeviceToHost, pipe_copy));
-      }
-      CUDA_CHECK(cudaStreamSynchronize(pipe_copy));
-      return;
+  constexpr int kPipe = 8;
+  u64 const rows_per = ((size + kPipe - 1) / kPipe + 31) & ~(u64)31;
+  if (cache_usable() && block == 1 && size >= (u64)1 << 20) {
+    // steady state: the streaming kernel runs row chunk by row chunk and the device-to-host copy
+    // of a finished chunk overlaps the kernel of the next one
+    if (!pipe_compute) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_compute, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaStreamCreateWithFlags(&pipe_copy, cudaStreamNonBlocking));
+      for (auto& e : pipe_events) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    matmat_device(dtype, block, dx.ptr, size, dy.ptr, size, nullptr);
-    CUDA_CHECK(cudaDeviceSynchronize());
-    CUDA_CHECK(cudaMemcpy2D(y, ys * es, dy.ptr, size * es, size * es, block, cudaMemcpyDeviceToHost));
+    // all kernels are queued first: a copy into pageable memory blocks the host, and must not
+    // keep the next chunk's kernel from being launched
+    int chunks = 0;
+    for (int c = 0; c < kPipe; ++c) {
+      u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
+      if (lo >= hi) break;
+      cached_matmat(dtype, 1, dx.ptr, size, dy.ptr, size, pipe_compute, lo, hi);
+      CUDA_CHECK(cudaEventRecord(pipe_events[c], pipe_compute));
+      chunks = c + 1;
+    }
+    for (int c = 0; c < chunks; ++c) {
+      u64 lo = std::min<u64>(size, (u64)c * rows_per), hi = std::min<u64>(size, lo + rows_per);
+      CUDA_CHECK(cudaStreamWaitEvent(pipe_copy, pipe_events[c], 0));
+      CUDA_CHECK(cudaMemcpyAsync(static_cast<unsigned char*>(y) + lo * es, dy.ptr + lo * es, (hi - lo) * es,
+                                 cudaMemcpyDeviceToHost, pipe_copy));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(pipe_copy));
     return;
   }
-  // per column: x -> [rank][local] layout, local rows of y computed in place inside a padded
-  // vector, all-gather, back to global order (written over the x column, which is no longer needed)
-  unsigned char* xp = dy.ptr;
-  unsigned char* yp = dy.ptr + padded * es;
-  for (u64 c = 0; c < block; ++c) {
-    unsigned char* col = dx.ptr + c * size * es;
-    convert_layout(true, es, col, xp, dist, cm.stream);
-    matmat_device(dtype, 1, xp, padded, yp + (u64)cm.rank * dist.chunk * es, padded, cm.stream);
-    comm_allgather_inplace(yp, dist.chunk * es, cm.stream);
-    convert_layout(false, es, yp, col, dist, cm.stream);
-  }
-  CUDA_CHECK(cudaStreamSynchronize(cm.stream));
-  CUDA_CHECK(cudaMemcpy2D(y, ys * es, dx.ptr, size * es, size * es, block, cudaMemcpyDeviceToHost));
+  matmat_device(dtype, block, dx.ptr, size, dy.ptr, size, nullptr);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  for (u64 c = 0; c < block; ++c)
+    CUDA_CHECK(cudaMemcpy(static_cast<unsigned char*>(y) + c * ys * es, dy.ptr + c * size * es, size * es, cudaMemcpyDeviceToHost));
 }
 
 template <class T>

@@ -16,14 +16,20 @@ def _device_count():
     return ffi.deviceCount()
 
 
+@pytest.mark.parametrize("shard_build", [False, True])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_build_matvec_and_eigh_match_oracle(world):
+def test_sharded_build_matvec_and_eigh_match_oracle(world, shard_build):
+    """shard_build: force the enumeration to be sharded over the ranks (small sectors are otherwise
+    enumerated redundantly by every rank, without communication)."""
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ)
+    if shard_build:
+        env["SPED_BUILD_SHARD_MIN"] = "0"
     names = ["heisenberg_chain_10", "heisenberg_square_4x4", "chain_8_k1_complex", "heisenberg_kagome_12",
              "heisenberg_square_5x5", "ring_4site_nosym"]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mp_worker.py")] + names
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)  # a collective mismatch hangs: fail fast
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)  # a collective mismatch hangs: fail fast
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MP_WORKER_OK" in out.stdout
