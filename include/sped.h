@@ -170,6 +170,15 @@ int sped_operator_matmat_device(void const* op, int dtype, uint64_t block_size, 
  * number of ranks, so results agree across rank counts to rounding, not bitwise. */
 int sped_operator_matvec_sharded(void const* op, int dtype, void const* x_local, void* y_local, void* x_replicated,
                                  void* stream);
+/* Host-pointer form of the row-sharded product, for a rank-parallel host eigensolver (PRIMME's
+ * parallel mode keeps nLocal rows per process): x_local / y_local are HOST blocks holding this
+ * rank's n_local rows (local order, see sped_row_distribution), column-major with the given
+ * strides.  Per column a rank sends n_local entries over PCIe, the shards are exchanged over NVLink
+ * inside the sharded product, and n_local entries come back -- unlike ls_operator_matmat, where
+ * every rank is handed the full x and receives the full y (/root/reference/src/SpinED/Internal.hs:411-429,
+ * a shared-memory reference has no notion of ranks).  With one rank the two calls coincide. */
+int sped_operator_matmat_local(void const* op, int dtype, uint64_t block_size, void const* x_local, uint64_t x_stride,
+                               void* y_local, uint64_t y_stride);
 /* Number of matrix elements one application touches: rows N and off-diagonal elements E
  * (term applications with non-zero target norm); global counts. */
 int sped_operator_count_elements(void const* op, uint64_t* rows, uint64_t* offdiag);

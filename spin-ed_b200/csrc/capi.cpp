@@ -297,6 +297,10 @@ int sped_operator_matvec_sharded(void const* op, int dtype, void const* x_local,
     from_handle<Operator>(op)->matvec_sharded(dtype, x_local, y_local, x_replicated, static_cast<cudaStream_t>(stream));
   });
 }
+int sped_operator_matmat_local(void const* op, int dtype, uint64_t block_size, void const* x_local, uint64_t x_stride,
+                               void* y_local, uint64_t y_stride) {
+  return guard([&] { from_handle<Operator>(op)->matmat_host_local(dtype, block_size, x_local, x_stride, y_local, y_stride); });
+}
 int sped_operator_count_elements(void const* op, uint64_t* rows, uint64_t* offdiag) {
   return guard([&] {
     u64 r, e;

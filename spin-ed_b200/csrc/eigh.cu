@@ -21,7 +21,140 @@ namespace sped {
 // ---------------------------------------------------------------------------------------------
 // small dense Hermitian eigenproblem (cyclic Jacobi), ascending eigenvalues, columns = vectors
 // ---------------------------------------------------------------------------------------------
+// Real symmetric case (every deck with real characters): Householder reduction to tridiagonal form
+// and the implicit QL iteration -- O(m^3) with a small constant, tens of microseconds for the
+// projected problems of the solver, where cyclic Jacobi in complex arithmetic took about a
+// millisecond per outer iteration.  a: row-major m x m, overwritten by the eigenvectors (columns);
+// d: eigenvalues (unsorted).  Returns false if the QL iteration does not converge.
+static bool symmetric_tridiagonal_eigh(int n, std::vector<double>& a, std::vector<double>& d) {
+  std::vector<double> e(n, 0.0);
+  d.assign(n, 0.0);
+  auto A = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };
+  // Householder reduction (rows n-1 .. 1), transformations accumulated in a
+  for (int i = n - 1; i > 0; --i) {
+    int const l = i - 1;
+    double h = 0, scale = 0;
+    if (l > 0) {
+      for (int k = 0; k <= l; ++k) scale += std::abs(A(i, k));
+      if (scale == 0.0) {
+        e[i] = A(i, l);
+      } else {
+        for (int k = 0; k <= l; ++k) {
+          A(i, k) /= scale;
+          h += A(i, k) * A(i, k);
+        }
+        double f = A(i, l);
+        double g = f >= 0 ? -std::sqrt(h) : std::sqrt(h);
+        e[i] = scale * g;
+        h -= f * g;
+        A(i, l) = f - g;
+        f = 0;
+        for (int j = 0; j <= l; ++j) {
+          A(j, i) = A(i, j) / h;
+          g = 0;
+          for (int k = 0; k <= j; ++k) g += A(j, k) * A(i, k);
+          for (int k = j + 1; k <= l; ++k) g += A(k, j) * A(i, k);
+          e[j] = g / h;
+          f += e[j] * A(i, j);
+        }
+        double const hh = f / (h + h);
+        for (int j = 0; j <= l; ++j) {
+          f = A(i, j);
+          e[j] = g = e[j] - hh * f;
+          for (int k = 0; k <= j; ++k) A(j, k) -= f * e[k] + g * A(i, k);
+        }
+      }
+    } else {
+      e[i] = A(i, l);
+    }
+    d[i] = h;
+  }
+  d[0] = 0;
+  e[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    int const l = i - 1;
+    if (d[i] != 0.0) {
+      for (int j = 0; j <= l; ++j) {
+        double g = 0;
+        for (int k = 0; k <= l; ++k) g += A(i, k) * A(k, j);
+        for (int k = 0; k <= l; ++k) A(k, j) -= g * A(k, i);
+      }
+    }
+    d[i] = A(i, i);
+    A(i, i) = 1.0;
+    for (int j = 0; j <= l; ++j) A(j, i) = A(i, j) = 0.0;
+  }
+  // implicit QL with Wilkinson shifts on (d, e), rotations applied to the columns of a
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0;
+  for (int l = 0; l < n; ++l) {
+    int iter = 0, mm;
+    do {
+      for (mm = l; mm < n - 1; ++mm) {
+        double const dd = std::abs(d[mm]) + std::abs(d[mm + 1]);
+        if (std::abs(e[mm]) <= 2.220446049250313e-16 * dd) break;
+      }
+      if (mm != l) {
+        if (iter++ == 80) return false;
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = std::hypot(g, 1.0);
+        g = d[mm] - d[l] + e[l] / (g + (g >= 0 ? std::abs(r) : -std::abs(r)));
+        double sn = 1, cs = 1, p = 0;
+        int i;
+        for (i = mm - 1; i >= l; --i) {
+          double f = sn * e[i];
+          double const b = cs * e[i];
+          e[i + 1] = r = std::hypot(f, g);
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[mm] = 0;
+            break;
+          }
+          sn = f / r;
+          cs = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * sn + 2.0 * cs * b;
+          p = sn * r;
+          d[i + 1] = g + p;
+          g = cs * r - b;
+          for (int k = 0; k < n; ++k) {
+            f = A(k, i + 1);
+            A(k, i + 1) = sn * A(k, i) + cs * f;
+            A(k, i) = cs * A(k, i) - sn * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[mm] = 0;
+      }
+    } while (mm != l);
+  }
+  return true;
+}
+
 void small_eigh(int m, std::vector<cplx> A /* row-major m x m */, std::vector<double>& evals, std::vector<cplx>& evecs) {
+  {  // real symmetric input: the fast path
+    bool real = true;
+    for (auto const& v : A) real = real && v.imag() == 0.0;
+    if (real && m > 0) {
+      std::vector<double> a((size_t)m * m), d;
+      for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) a[(size_t)i * m + j] = 0.5 * (A[(size_t)i * m + j].real() + A[(size_t)j * m + i].real());
+      if (symmetric_tridiagonal_eigh(m, a, d)) {
+        std::vector<int> order(m);
+        for (int i = 0; i < m; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return d[x] < d[y]; });
+        evals.resize(m);
+        evecs.assign((size_t)m * m, cplx(0, 0));
+        for (int k = 0; k < m; ++k) {
+          evals[k] = d[order[k]];
+          for (int i = 0; i < m; ++i) evecs[(size_t)i * m + k] = a[(size_t)i * m + order[k]];
+        }
+        return;
+      }
+    }
+  }
   std::vector<cplx> V((size_t)m * m, cplx(0, 0));
   for (int i = 0; i < m; ++i) V[(size_t)i * m + i] = 1.0;
   auto at = [&](int i, int j) -> cplx& { return A[(size_t)i * m + j]; };
@@ -318,6 +451,80 @@ __global__ void __launch_bounds__(kThreads) scale_kernel(T* w, u64 n, double2 co
     VT<T>::store(w + i, mulc(VT<T>::load(w + i), make_double2(s, 0)));
 }
 
+// Cholesky factor of the Gram matrix G = W^H W of a group of nw <= 4 vectors (G row-major,
+// G[j * nw + c] = <w_j, w_c>), one thread: G = R^H R, and the inverse of the upper-triangular R, so
+// that W R^{-1} has orthonormal columns (CholQR; the DGKS flag below makes it CholQR2 when needed).
+// record[c] = R_cc^2 = squared norm of w_c after the components along w_0..w_{c-1} are removed;
+// a column with R_cc^2 <= tiny is linearly dependent: it becomes the zero vector.  *flag is
+// raised when some column kept less than half of its (unit) length.
+__global__ void chol_kernel(double2 const* G, int nw, double2* Rinv, double tiny, double* record, int* flag, int const* gate) {
+  if (gate && *gate == 0) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double2 R[4][4], X[4][4];
+  bool dead[4];
+  auto cm = [](double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); };
+  auto cj = [](double2 a) { return make_double2(a.x, -a.y); };
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) R[i][j] = X[i][j] = make_double2(0, 0);
+  for (int c = 0; c < nw; ++c) {
+    // column c of R: R_jc = (G_jc - sum_{k<j} conj(R_kj) R_kc) / R_jj
+    for (int j = 0; j < c; ++j) {
+      double2 v = G[j * nw + c];
+      for (int k = 0; k < j; ++k) {
+        double2 t = cm(cj(R[k][j]), R[k][c]);
+        v.x -= t.x;
+        v.y -= t.y;
+      }
+      R[j][c] = dead[j] ? make_double2(0, 0) : make_double2(v.x / R[j][j].x, v.y / R[j][j].x);
+    }
+    double d = G[c * nw + c].x;
+    for (int k = 0; k < c; ++k) d -= R[k][c].x * R[k][c].x + R[k][c].y * R[k][c].y;
+    dead[c] = !(d > tiny);
+    R[c][c] = make_double2(dead[c] ? 1.0 : sqrt(d), 0);
+    if (record) record[c] = d;
+    if (flag && d < 0.5) *flag = 1;
+  }
+  // X = R^{-1} (upper triangular) by back substitution, column by column; dead columns are zero
+  for (int c = 0; c < nw; ++c) {
+    if (dead[c]) continue;
+    X[c][c] = make_double2(1.0 / R[c][c].x, 0);
+    for (int i = c - 1; i >= 0; --i) {
+      double2 v = make_double2(0, 0);
+      for (int k = i + 1; k <= c; ++k) {
+        double2 t = cm(R[i][k], X[k][c]);
+        v.x -= t.x;
+        v.y -= t.y;
+      }
+      X[i][c] = make_double2(v.x / R[i][i].x, v.y / R[i][i].x);
+    }
+  }
+  for (int i = 0; i < nw; ++i)
+    for (int c = 0; c < nw; ++c) Rinv[i * nw + c] = X[i][c];
+}
+
+// W <- W X for an nw x nw matrix X (row-major), in place, row by row
+template <class T, int NW>
+__global__ void __launch_bounds__(kThreads) right_multiply_kernel(T* W, u64 ldw, u64 n, double2 const* X, int const* gate) {
+  using A = typename VT<T>::Acc;
+  if (gate && *gate == 0) return;
+  __shared__ double2 x[NW * NW];
+  if (threadIdx.x < NW * NW) x[threadIdx.x] = X[threadIdx.x];
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    A row[NW], out[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) row[j] = VT<T>::load(W + (u64)j * ldw + i);
+#pragma unroll
+    for (int c = 0; c < NW; ++c) {
+      out[c] = from2<A>(make_double2(0, 0));
+#pragma unroll
+      for (int j = 0; j <= c; ++j) out[c] = addv(out[c], mulc(row[j], x[j * NW + c]));
+    }
+#pragma unroll
+    for (int c = 0; c < NW; ++c) VT<T>::store(W + (u64)c * ldw + i, out[c]);
+  }
+}
+
 // out_q = sum_j (W_j - theta_q V_j) s[j * KQ + q] for q < KQ in ONE pass over V and W;
 // partial[q * gridDim.x + block] = sum |out_q|^2
 template <class T, int KQ>
@@ -508,25 +715,26 @@ struct Solver {
   }
 
   // One sweep of the block orthogonalisation of W[:, 0:nw) (unit-length columns on entry of the
-  // first sweep): against V[:, 0:m) -- V read once for the whole group -- then column by column
-  // inside the group; every column ends normalised, its squared norm BEFORE the scaling recorded
-  // in norms_out[c].  first sweep: `raise` is set when some column kept less than half of its
+  // first sweep): against V[:, 0:m) -- V read once for the whole group -- then inside the group by
+  // CholQR; every column ends normalised, its squared norm BEFORE the scaling (after the removal
+  // of the components along V and along the earlier columns of the group) recorded in norms_out[c].  first sweep: `raise` is set when some column kept less than half of its
   // length (DGKS: a second sweep is due); second sweep: every kernel is gated on that flag.
   void ortho_sweep(int m, T* W, int nw, double* norms_out, int* raise, int const* gate) {
     if (m > 0) {
       block_dots(V.ptr, m, W, nw, coeff.ptr, gate);
       block_axpy(V.ptr, m, coeff.ptr, W, nw, gate);
     }
-    for (int c = 0; c < nw; ++c) {
-      T* wc = W + (u64)c * ld;
-      block_dots(wc, 1, wc, 1, scal.ptr, gate);
-      scale_kernel<T><<<grid, kThreads, 0, stream>>>(wc, n, scal.ptr, 1e-24, norms_out ? norms_out + c : nullptr, raise, gate);
-      KERNEL_LAUNCHED();
-      if (c + 1 < nw) {
-        block_dots(wc, 1, wc + ld, nw - 1 - c, coeff.ptr, gate);
-        block_axpy(wc, 1, coeff.ptr, wc + ld, nw - 1 - c, gate);
-      }
+    // inside the group: Gram matrix, Cholesky factor on the device, W <- W R^{-1}
+    block_dots(W, nw, W, nw, scal.ptr, gate);
+    chol_kernel<<<1, 32, 0, stream>>>(scal.ptr, nw, scal.ptr + 16, 1e-24, norms_out, raise, gate);
+    KERNEL_LAUNCHED();
+    switch (nw) {
+      case 1: right_multiply_kernel<T, 1><<<grid, kThreads, 0, stream>>>(W, ld, n, scal.ptr + 16, gate); break;
+      case 2: right_multiply_kernel<T, 2><<<grid, kThreads, 0, stream>>>(W, ld, n, scal.ptr + 16, gate); break;
+      case 3: right_multiply_kernel<T, 3><<<grid, kThreads, 0, stream>>>(W, ld, n, scal.ptr + 16, gate); break;
+      default: right_multiply_kernel<T, 4><<<grid, kThreads, 0, stream>>>(W, ld, n, scal.ptr + 16, gate); break;
     }
+    KERNEL_LAUNCHED();
   }
 
   // New search directions W[:, 0:nw) (columns of V past the first m), unit length on entry:

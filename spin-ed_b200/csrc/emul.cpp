@@ -171,9 +171,9 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
     table[3 * c + 1] = vy;
     table[3 * c + 2] = pr.sym ? pr.norm_table[cm.sid_stab[sid]] : 1.0;
   }
-  u32 const rounds = (u32)exchange_rounds(d.world);
+  u32 const rounds = (u32)exchange_rounds(d.world, d.chunk);
   u32 const n_classes = 1u + rounds;
-  u32 const near = exchange_near(d.world);
+  u32 const near = exchange_near(d.world, d.chunk);
   bool const wide = cm.n_codes > 256;
   u64 const n_slices = (n_local + 31) / 32;
   std::vector<std::uint16_t> len(std::max<u64>(n_local, 1) * 2 * n_classes, 0);

@@ -261,12 +261,14 @@ struct Operator {
   void prepare();
   void matmat_device(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s);
   void matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs, void* y, u64 ys);
+  // host blocks of this rank's rows only (sped_operator_matmat_local)
+  void matmat_host_local(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys);
   void expectation_host(int dtype, u64 size, u64 block, void const* x, u64 xs, cplx* out);
   void count_elements(u64& rows, u64& offdiag);
 };
 
-int exchange_rounds(unsigned world);  // opcache.cu
-unsigned exchange_near(unsigned world);
+int exchange_rounds(unsigned world, u64 chunk);  // opcache.cu
+unsigned exchange_near(unsigned world, u64 chunk);
 
 // Code maps of the operator cache (opcache.cu, build_code_maps)
 struct CodeMaps {

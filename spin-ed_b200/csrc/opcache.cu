@@ -245,12 +245,20 @@ int env_cache_mode() {
 }  // namespace
 
 // Number of exchange rounds of a sharded matvec (and remote source classes of the cache): a function
-// of the world size and the environment only, so that every rank makes the same choice.
-// SPED_REMOTE_GROUPS=1: one round (NCCL all-gather) even with more than two ranks.
-int exchange_rounds(unsigned world) {
+// of the world size, the shard length and the environment only, so that every rank makes the same
+// choice.  Two rounds (grouped NCCL send/recv, near peers first) let the pass over the first group's
+// elements overlap the second transfer, which pays when the transfers are long (40-spin chains:
+// gigabytes per shard); shards below 2^23 entries (6x6 over 4-8 ranks: 16-32 MB) are latency-bound
+// and go through ONE NCCL all-gather, which is much faster than grouped point-to-point calls there
+// (measured on 4 B200: 0.21 ms for the all-gather against 0.22 + 0.25 ms for the two rounds).
+// SPED_REMOTE_GROUPS=1 / 2 forces one / two rounds.
+int exchange_rounds(unsigned world, u64 chunk) {
   if (world <= 1) return 0;
+  if (world == 2) return 1;
   char const* e = std::getenv("SPED_REMOTE_GROUPS");
-  return (world == 2 || (e && e[0] == '1')) ? 1 : 2;
+  if (e && e[0] == '1') return 1;
+  if (e && e[0] == '2') return 2;
+  return chunk >= ((u64)1 << 23) ? 2 : 1;
 }
 
 // Coefficient codes of the operator cache: code = (hid * n_pid + pid) * n_sid + sid with hid the
@@ -331,7 +339,7 @@ char const* build_code_maps(Operator const& op, CodeMaps& out) {
 
 // Peers of the first exchange round: ranks r+1 .. r+near (a function of the world size and the
 // environment only, like exchange_rounds: every rank must agree on who talks in which round).
-unsigned exchange_near(unsigned world) { return exchange_rounds(world) == 2 ? world / 2 : world - 1; }
+unsigned exchange_near(unsigned world, u64 chunk) { return exchange_rounds(world, chunk) == 2 ? world / 2 : world - 1; }
 
 void Operator::drop_cache() {
   cache_ready = false;
@@ -397,9 +405,9 @@ bool Operator::cache_usable() {
   u64 const code_bytes = c_code_wide ? 2 : 1;
   // source classes (see CacheView): local / peers of the first exchange round / of the second
   u32 const world = dist.world;
-  c_rounds = (u32)exchange_rounds(world);
+  c_rounds = (u32)exchange_rounds(world, dist.chunk);
   c_classes = 1 + c_rounds;
-  c_near = exchange_near(world);  // 8 ranks: 4 peers in the first round, 3 in the second
+  c_near = exchange_near(world, dist.chunk);  // 8 ranks: 4 peers in the first round, 3 in the second
   bool const two = c_rounds > 0;  // several ranks: exact class sizes from a counting traversal
   MatvecParams mp = operator_params(*this);
   size_t tsm = terms_smem_bytes(mp.terms, false);
@@ -472,7 +480,10 @@ bool Operator::cache_usable() {
   u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 16 : 8) + n_codes * 24;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-  if (mode != 1 && need > free_b / 2) return reject("does not fit in half of the free device memory");
+  // automatic mode keeps room for what a solver typically allocates afterwards (a few more vectors of
+  // the local rows); mode 1 only insists on the cache itself fitting
+  u64 const reserve = std::max<u64>((u64)2 << 30, 4 * n_local * 16);
+  if (mode != 1 && need + reserve > free_b) return reject("does not fit in the free device memory (with room for the solver's vectors)");
   if (need > free_b - free_b / 16) return reject("does not fit in device memory");
   c_idx.alloc(std::max<u64>(c_slots, 1));
   c_code.alloc(std::max<u64>(c_slots, 1) * code_bytes);

@@ -420,7 +420,7 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
     matmat_device(dtype, 1, xfull, padded, y_local, std::max<u64>(n_local, 1), s);
     return;
   }
-  bool const rounds = exchange_rounds(dist.world) == 2;
+  bool const rounds = exchange_rounds(dist.world, dist.chunk) == 2;
   bool const cached = n_local > 0 && cache_usable() && c_rounds == (rounds ? 2u : 1u);
   // SPED_OVERLAP_TRACE=n: device times of the first n overlapped matvecs
   static int trace_left = [] {
@@ -442,7 +442,7 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
   if (rounds) {
     // (near comes from the world size, not from this rank's cache: a rank without rows or without a
     // cache has to send and receive in the same rounds as everybody else)
-    int const near = (int)exchange_near(dist.world);
+    int const near = (int)exchange_near(dist.world, dist.chunk);
     comm_exchange_round(xfull, dist.chunk * es, 1, near, g);
     CUDA_CHECK(cudaEventRecord(cm.ev_round1, g));
     mark(1, g);
@@ -665,6 +665,34 @@ void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs
   CUDA_CHECK(cudaDeviceSynchronize());
   for (u64 c = 0; c < block; ++c)
     CUDA_CHECK(cudaMemcpy(static_cast<unsigned char*>(y) + c * ys * es, dy.ptr + c * size * es, size * es, cudaMemcpyDeviceToHost));
+}
+
+// Row-sharded host-pointer entry: this rank's rows in, this rank's rows out (see sped.h).
+void Operator::matmat_host_local(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys) {
+  prepare();
+  Comm& cm = comm();
+  if (!cm.active()) {
+    matmat_host(dtype, basis->n_states, block, x, xs, y, ys);
+    return;
+  }
+  if (!dtype_is_complex(dtype) && !is_real()) fail(LS_OPERATOR_IS_COMPLEX, "operator is complex but a real datatype was requested");
+  u64 const n_local = dist.n_local, padded = dist.chunk * dist.world;
+  if (xs < n_local || ys < n_local) fail(LS_INVALID_ARGUMENT, "strides must be at least the number of local rows");
+  if (block == 0) return;
+  size_t const es = dtype_size(dtype);
+  if (stage_y.count < 2 * padded * es) stage_y.alloc(2 * padded * es);
+  unsigned char* xp = stage_y.ptr;
+  unsigned char* yl = stage_y.ptr + padded * es;  // local rows of the result
+  unsigned char* mine = xp + (u64)dist.rank * dist.chunk * es;
+  cudaStream_t st = cm.stream;
+  for (u64 c = 0; c < block; ++c) {
+    if (n_local)
+      CUDA_CHECK(cudaMemcpyAsync(mine, static_cast<unsigned char const*>(x) + c * xs * es, n_local * es, cudaMemcpyHostToDevice, st));
+    matvec_sharded(dtype, mine, yl, xp, st);
+    if (n_local)
+      CUDA_CHECK(cudaMemcpyAsync(static_cast<unsigned char*>(y) + c * ys * es, yl, n_local * es, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 template <class T>

@@ -112,6 +112,7 @@ SIGNATURES = {
     "sped_basis_program_stats": (_ci, [_vp, C.POINTER(_cu), C.POINTER(_cu), C.POINTER(_cu)]),
     "sped_operator_matmat_device": (_ci, [_vp, _ci, _u64, _vp, _u64, _vp, _u64, _vp]),
     "sped_operator_matvec_sharded": (_ci, [_vp, _ci, _vp, _vp, _vp, _vp]),
+    "sped_operator_matmat_local": (_ci, [_vp, _ci, _u64, _vp, _u64, _vp, _u64]),
     "sped_operator_count_elements": (_ci, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "sped_operator_diagonal": (_ci, [_vp, _vp]),
     "sped_operator_set_cache": (_ci, [_vp, _ci]),
@@ -479,6 +480,20 @@ def operatorMatmatDevice(op: Operator, dtype_tag: int, block: int, x_ptr: int, x
 def operatorMatvecSharded(op: Operator, dtype_tag: int, x_local_ptr: int, y_local_ptr: int, x_replicated_ptr: int, stream: int = 0):
     """One column from this rank's shard: all-gather (library stream) overlapped with the local-source pass."""
     checkStatus(lib().sped_operator_matvec_sharded(op._ptr, dtype_tag, x_local_ptr, y_local_ptr, x_replicated_ptr, stream))
+
+
+def applyLocal(op: Operator, x_local: np.ndarray, y_local: np.ndarray):
+    """Row-sharded host-pointer product: this rank's rows of x in, this rank's rows of y out
+    (1-D arrays or column-major blocks of n_local rows)."""
+    xb, yb = np.asarray(x_local), np.asarray(y_local)
+    if xb.dtype != yb.dtype or xb.shape != yb.shape:
+        raise SpinEDException("x and y must have the same shape and dtype")
+    rows = xb.shape[0] if xb.ndim else 0
+    cols = xb.shape[1] if xb.ndim == 2 else 1
+    if xb.ndim == 2 and not (xb.flags.f_contiguous and yb.flags.f_contiguous):
+        raise SpinEDException("blocks must be column-major")
+    checkStatus(lib().sped_operator_matmat_local(op._ptr, DTYPE_TAGS[xb.dtype], cols, xb.ctypes.data, max(rows, 1),
+                                                 yb.ctypes.data, max(rows, 1)))
 
 
 def operatorCountElements(op: Operator):

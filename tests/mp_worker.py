@@ -68,6 +68,13 @@ def main():
             if len(mine):
                 diff = np.linalg.norm(ylocal[:len(mine)].cpu().numpy() - want[mine, 0])
                 assert diff <= 1e-12 * np.linalg.norm(want[:, 0]), (name, mode, diff)
+        # row-sharded host-pointer entry (a rank-parallel host solver): local rows in, local rows out
+        ffi.operatorSetCache(op, -1)
+        xl = np.asfortranarray(x[mine, :])
+        yl = np.full_like(xl, 7.0)
+        ffi.applyLocal(op, xl, yl)
+        if len(mine):
+            assert np.linalg.norm(yl - want[mine, :]) <= 1e-12 * np.linalg.norm(want), name
         rows, n_off = ffi.operatorCountElements(op)
         assert (rows, n_off) == (n, oop.count_offdiag())
         ex = ffi.expectation(op, x)

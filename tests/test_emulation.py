@@ -13,8 +13,6 @@ import pytest
 from helpers import SMALL_DECKS, extra_configs, oracle_problem, product_problem, splitmix_vector
 from spin_ed_b200 import decks, ffi
 
-ONE_ROUND = os.environ.get("SPED_REMOTE_GROUPS", "") == "1"  # one exchange round (all-gather) even for > 2 ranks
-
 NAMES = SMALL_DECKS + ["chain_12_full_sym", "chain_12_pi", "chain_8_k1_complex", "chain_9_k2_nohw", "chain_10_inv_only",
                        "chain_10_inv_nohw", "chain_8_chiral_3site", "ring_4site_nosym", "chain_40_hw3_k"]
 
@@ -36,8 +34,13 @@ def _emulate(op, reps, stab, world, rank, x, ncols=1):
     return rows, [o[:n_local] for o in outs], [int(v) for v in stats]
 
 
+@pytest.mark.parametrize("groups", ["1", "2"])
 @pytest.mark.parametrize("name", NAMES)
-def test_emulated_kernels_match_oracle(oracle, name):
+def test_emulated_kernels_match_oracle(oracle, name, groups, monkeypatch):
+    # exchange rounds for > 2 ranks: shards this small would take one round (all-gather); both the
+    # two-class and the three-class layout are forced in turn
+    monkeypatch.setenv("SPED_REMOTE_GROUPS", groups)
+    ONE_ROUND = groups == "1"
     cfg = extra_configs()[name] if name in extra_configs() else decks.load(name)
     ob, terms = oracle_problem(oracle, cfg)
     ob.build()

@@ -180,6 +180,41 @@ def test_small_eigh_matches_numpy(m, cplx):
     assert np.allclose(V.conj().T @ V, np.eye(m), atol=1e-12)
 
 
+@pytest.mark.parametrize("kind", ["diagonal", "degenerate", "arrow", "graded", "identity"])
+def test_small_eigh_real_fast_path_on_structured_matrices(kind):
+    """The projected matrices of the solver are far from generic: diagonal Ritz blocks bordered by
+    new rows (arrow shape), exactly degenerate levels, entries spread over many orders of magnitude."""
+    rng = np.random.default_rng(3)
+    m = 24
+    if kind == "diagonal":
+        A = np.diag(np.sort(rng.standard_normal(m)))
+    elif kind == "identity":
+        A = np.eye(m)
+    elif kind == "degenerate":
+        q, _ = np.linalg.qr(rng.standard_normal((m, m)))
+        A = q @ np.diag(np.repeat([-8.0, -3.0, 0.0, 5.0], 6)) @ q.T
+    elif kind == "arrow":
+        A = np.diag(np.sort(rng.standard_normal(m)) * 10)
+        A[:, -3:] = 1e-7 * rng.standard_normal((m, 3))
+        A[-3:, :] = A[:, -3:].T
+        A[-3:, -3:] = np.diag([1.0, 2.0, 3.0])
+    else:
+        s = 10.0 ** rng.uniform(-9, 2, m)
+        B = rng.standard_normal((m, m))
+        A = s[:, None] * (B + B.T) * s[None, :]
+    A = (A + A.T) / 2
+    a = np.ascontiguousarray(A.astype(np.complex128))
+    ev = np.zeros(m)
+    V = np.zeros((m, m), dtype=np.complex128)
+    ffi.checkStatus(ffi.lib().sped_selftest_small_eigh(m, a.ctypes.data, ev.ctypes.data, V.ctypes.data))
+    scale = max(1.0, np.abs(A).max())
+    assert np.all(np.diff(ev) >= 0)
+    assert np.allclose(ev, np.linalg.eigvalsh(A), atol=1e-12 * scale)
+    assert np.allclose(A @ V, V * ev, atol=1e-11 * scale)
+    assert np.allclose(V.conj().T @ V, np.eye(m), atol=1e-12)
+    assert np.all(V.imag == 0)
+
+
 def test_row_distribution_is_a_balanced_block_cyclic_partition():
     import ctypes as C
 

@@ -20,12 +20,14 @@ def _device_count():
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_build_matvec_and_eigh_match_oracle(world, shard_build):
     """shard_build: force the enumeration to be sharded over the ranks (small sectors are otherwise
-    enumerated redundantly by every rank, without communication)."""
+    enumerated redundantly by every rank, without communication) and force two exchange rounds with
+    three source classes (shards this small would otherwise take one NCCL all-gather)."""
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ)
     if shard_build:
         env["SPED_BUILD_SHARD_MIN"] = "0"
+        env["SPED_REMOTE_GROUPS"] = "2"
     names = ["heisenberg_chain_10", "heisenberg_square_4x4", "chain_8_k1_complex", "heisenberg_kagome_12",
              "heisenberg_square_5x5", "ring_4site_nosym"]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
