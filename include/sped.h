@@ -213,6 +213,10 @@ typedef int (*sped_monitor_fn)(sped_eigh_info const* info, void* ctx); /* non-ze
 int sped_eigh(void const* op, int dtype, uint64_t n_evals, double eps, int max_basis_size, int max_block_size,
               int min_restart_size, double* evals, void* evecs, double* rnorms, sped_monitor_fn monitor,
               void* ctx);
+/* sped_eigh keeps its device workspace (Krylov basis, H V, residuals) on the operator between calls
+ * -- freeing and re-allocating gigabytes costs more wall time than a warm 6x6 solve.  This releases
+ * it (it is also released with the operator). */
+int sped_operator_release_workspace(void const* op);
 /* Statistics of the last sped_eigh call on this operator. */
 typedef struct sped_eigh_stats {
   uint64_t matvecs;

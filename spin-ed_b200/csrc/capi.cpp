@@ -344,6 +344,9 @@ int sped_eigh(void const* op, int dtype, uint64_t n_evals, double eps, int max_b
   });
   return rc != LS_SUCCESS ? rc : status;
 }
+int sped_operator_release_workspace(void const* op) {
+  return guard([&] { from_handle<Operator>(op)->release_workspace(); });
+}
 int sped_eigh_last_stats(void const* op, sped_eigh_stats* out) {
   return guard([&] {
     auto& s = from_handle<Operator>(op)->last_stats;

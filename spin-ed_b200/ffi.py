@@ -118,6 +118,7 @@ SIGNATURES = {
     "sped_operator_set_cache": (_ci, [_vp, _ci]),
     "sped_operator_cache_info": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_u64), C.POINTER(C.c_double)]),
     "sped_eigh": (_ci, [_vp, _ci, _u64, C.c_double, _ci, _ci, _ci, _vp, _vp, _vp, MONITOR_FN, _vp]),
+    "sped_operator_release_workspace": (_ci, [_vp]),
     "sped_eigh_last_stats": (_ci, [_vp, C.POINTER(sped_eigh_stats)]),
     "sped_selftest_small_eigh": (_ci, [_ci, _vp, _vp, _vp]),
     "sped_selftest_program": (_ci, [_vp, _u64, _vp, _vp, _vp, _vp]),
@@ -543,6 +544,11 @@ def eigh(op: Operator, dtype, numEvals=1, eps=0.0, maxBasisSize=0, maxBlockSize=
                          evecs.ctypes.data if want_vectors else None, rnorms.ctypes.data, cb, None)
     checkStatus(rc)
     return evals, evecs, rnorms
+
+
+def operatorReleaseWorkspace(op: Operator):
+    """Free the device workspace sped_eigh keeps on the operator between calls."""
+    checkStatus(lib().sped_operator_release_workspace(op._ptr))
 
 
 def eighLastStats(op: Operator) -> dict:
