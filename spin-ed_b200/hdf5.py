@@ -12,11 +12,17 @@ table B-tree + local heap, contiguous dataset layout).  Layout written, as the r
     /observables/<name>           complex128 [k]  (compound {r, i}; hdf5-hs's own choice is unpinned)
     /_workspace                   (empty group)
 
-Status: validated by round trip through the reader below (tests/test_driver_cpu.py); it has NOT
-been opened with libhdf5 here because none is available -- stated in DESIGN.md.
+Status: validated by round trip through the reader below and by a second, independently written
+spec-level reader/validator (tests/h5_spec_reader.py, tests/test_driver_cpu.py); it has NOT been
+opened with libhdf5 here because none is available -- stated in DESIGN.md.
 
-The file is opened "WriteAppend" like the reference (SpinED.hs:287): existing content is read,
-datasets are added or overwritten, and the whole file is rewritten on close.
+The file is opened "WriteAppend" like the reference (SpinED.hs:287).  Opening reads only the
+metadata: datasets stay on disk as read-only memory maps (40/42-spin representatives are 7-26 GB).
+Closing a modified file APPENDS -- the raw data of new datasets, then a fresh copy of the (few KB
+of) metadata: object headers, local heaps, B-tree and symbol-table nodes -- and finally patches the
+end-of-file address and the root symbol-table entry in the superblock.  Raw data already in the
+file is never read, moved or rewritten; superseded metadata and deleted datasets become unreferenced
+space, as they do with libhdf5 until a repack.  A file that was only read is not touched.
 """
 from __future__ import annotations
 
@@ -90,21 +96,42 @@ def _parse_dtype(buf: bytes, off: int = 0):
 # in-memory tree
 # ------------------------------------------------------------------------------------------
 class Group(OrderedDict):
-    """name -> Group | numpy array"""
+    """name -> Group | numpy array (new data) | _Stored (data already in the file)"""
+
+
+class _Stored:
+    """A dataset whose raw data already lives in the file: address, shape, dtype; mapped on demand."""
+
+    def __init__(self, path, addr, shape, dtype):
+        self.path, self.addr, self.shape, self.dtype = path, int(addr), tuple(int(d) for d in shape), np.dtype(dtype)
+
+    @property
+    def nbytes(self):
+        return int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+
+    def array(self):
+        if self.nbytes == 0:
+            return np.zeros(self.shape, dtype=self.dtype)
+        return np.memmap(self.path, dtype=self.dtype, mode="r", offset=self.addr, shape=self.shape)
 
 
 class File:
     def __init__(self, path: str, mode: str = "a"):
         self.path = path
         self.root = Group()
+        self.dirty = False
+        self.existing = False
         if mode in ("a", "r") and os.path.exists(path) and os.path.getsize(path) > 0:
             self.root = _read_file(path)
+            self.existing = True
         elif mode == "r":
             raise FileNotFoundError(path)
+        else:
+            self.dirty = True  # a new file is written even when it stays empty
         self.mode = mode
 
     # --- h5py-like helpers -----------------------------------------------------------------
-    def _walk(self, path: str, create: bool):
+    def _walk_impl(self, path: str, create: bool):
         node = self.root
         parts = [p for p in path.split("/") if p]
         for p in parts[:-1]:
@@ -128,24 +155,38 @@ class File:
         node, leaf = self._walk(path, True)
         if leaf and leaf not in node:
             node[leaf] = Group()
+            self.dirty = True
+
+    def _walk(self, path: str, create: bool):
+        before = _count_groups(self.root) if create else 0
+        out = self._walk_impl(path, create)
+        if create and _count_groups(self.root) != before:
+            self.dirty = True
+        return out
 
     def write_dataset(self, path: str, array):
         node, leaf = self._walk(path, True)
         node[leaf] = np.ascontiguousarray(array)
+        self.dirty = True
 
     def read_dataset(self, path: str) -> np.ndarray:
+        """The dataset as an array; data already in the file comes back as a read-only memory map."""
         node, leaf = self._walk(path, False)
         if leaf not in node or isinstance(node[leaf], Group):
             raise KeyError(path)
-        return node[leaf]
+        v = node[leaf]
+        return v.array() if isinstance(v, _Stored) else v
 
     def delete(self, path: str):
         node, leaf = self._walk(path, False)
         del node[leaf]
+        self.dirty = True
 
     def close(self):
-        if self.mode != "r":
-            _write_file(self.path, self.root)
+        if self.mode != "r" and self.dirty:
+            _write_file(self.path, self.root, append=self.existing)
+            self.dirty = False
+            self.existing = True
 
     def __enter__(self):
         return self
@@ -155,13 +196,17 @@ class File:
             self.close()
 
 
+def _count_groups(g: Group) -> int:
+    return 1 + sum(_count_groups(c) for c in g.values() if isinstance(c, Group))
+
+
 # ------------------------------------------------------------------------------------------
 # writer
 # ------------------------------------------------------------------------------------------
 class _Writer:
-    def __init__(self):
+    def __init__(self, start: int = 96):
         self.chunks = []  # (address, bytes | ndarray)
-        self.pos = 96     # superblock occupies [0, 96)
+        self.pos = start  # a new file: the superblock occupies [0, 96); appending: the old end of file
 
     def alloc(self, size: int) -> int:
         self.pos = (self.pos + 7) // 8 * 8
@@ -182,14 +227,18 @@ class _Writer:
         self.put(addr, hdr)
         return addr
 
-    def dataset(self, arr: np.ndarray) -> int:
-        arr = np.ascontiguousarray(arr)
-        shape = arr.shape if arr.ndim else (1,)
-        data_addr = self.alloc(max(arr.nbytes, 1))
-        self.put(data_addr, arr)
+    def dataset(self, arr) -> int:
+        if isinstance(arr, _Stored):  # raw data stays where it is; only the (small) header is written anew
+            shape, dtype, nbytes, data_addr = arr.shape, arr.dtype, arr.nbytes, arr.addr
+        else:
+            arr = np.ascontiguousarray(arr)
+            shape = arr.shape if arr.ndim else (1,)
+            dtype, nbytes = arr.dtype, arr.nbytes
+            data_addr = self.alloc(max(arr.nbytes, 1))
+            self.put(data_addr, arr)
         space = struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", d) for d in shape)
-        layout = struct.pack("<BBQQ", 3, 1, data_addr, arr.nbytes)
-        return self.object_header([(0x0001, space), (0x0003, _dtype_message(arr.dtype)), (0x0008, layout)])
+        layout = struct.pack("<BBQQ", 3, 1, data_addr, nbytes)
+        return self.object_header([(0x0001, space), (0x0003, _dtype_message(dtype)), (0x0008, layout)])
 
     def group(self, g: Group):
         """-> (object header address, btree address, heap address)"""
@@ -239,18 +288,27 @@ class _Writer:
         return oh, bt_addr, heap_addr
 
 
-def _write_file(path: str, root: Group):
-    w = _Writer()
-    oh, bt, hp = w.group(root)
-    eof = (w.pos + 7) // 8 * 8
+def _superblock(eof: int, oh: int, bt: int, hp: int) -> bytes:
     sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, LEAF_K, INTERNAL_K, 0)
     sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
     sb += struct.pack("<QQI4xQQ", 0, oh, 1, bt, hp)
     assert len(sb) == 96
-    tmp = path + ".tmp"
+    return sb
+
+
+def _write_file(path: str, root: Group, append: bool = False):
+    """append: new raw data and a fresh copy of all metadata go behind the current end of file, then
+    the superblock is patched (last, so that an interrupted write leaves the old file readable)."""
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    with open(tmp, "wb") as f:
-        f.write(sb)
+    start = 96
+    if append:
+        start = (os.path.getsize(path) + 7) // 8 * 8
+    w = _Writer(start)
+    oh, bt, hp = w.group(root)
+    eof = (w.pos + 7) // 8 * 8
+    with open(path, "r+b" if append else "wb") as f:
+        if not append:
+            f.write(b"\0" * 96)
         for addr, data in sorted(w.chunks, key=lambda c: c[0]):
             f.seek(addr)
             if isinstance(data, np.ndarray):
@@ -258,7 +316,12 @@ def _write_file(path: str, root: Group):
             else:
                 f.write(data)
         f.truncate(eof)
-    os.replace(tmp, path)
+        f.flush()
+        os.fsync(f.fileno())
+        f.seek(0)
+        f.write(_superblock(eof, oh, bt, hp))
+        f.flush()
+        os.fsync(f.fileno())
 
 
 # ------------------------------------------------------------------------------------------
@@ -276,18 +339,26 @@ def _read_file(path: str) -> Group:
 
 
 def _read_messages(f, addr: int):
+    """Messages of a version-1 object header, following continuation messages (0x0010) into their blocks."""
     f.seek(addr)
     version, _, nmsg, _, size = struct.unpack("<BBHII", f.read(12))
     if version != 1:
         raise ValueError("only version-1 object headers are supported")
     f.read(4)
-    body = f.read(size)
-    out, p = [], 0
-    while p + 8 <= len(body) and len(out) < nmsg:
-        mtype, msize, _ = struct.unpack_from("<HHB", body, p)
-        out.append((mtype, body[p + 8:p + 8 + msize]))
-        p += 8 + msize
-    return out
+    blocks = [f.read(size)]
+    out = []
+    while blocks and len(out) < nmsg:
+        body, p = blocks.pop(0), 0
+        while p + 8 <= len(body) and len(out) < nmsg:
+            mtype, msize, _ = struct.unpack_from("<HHB", body, p)
+            data = body[p + 8:p + 8 + msize]
+            out.append((mtype, data))
+            if mtype == 0x0010:  # object header continuation: (offset, length) of another block of messages
+                c_off, c_len = struct.unpack_from("<QQ", data)
+                f.seek(c_off)
+                blocks.append(f.read(c_len))
+            p += 8 + msize
+    return [(t, d) for t, d in out if t != 0x0010]
 
 
 def _read_group(f, oh_addr: int) -> Group:
@@ -337,6 +408,5 @@ def _read_group(f, oh_addr: int) -> Group:
         if layout[0] != 3 or layout[1] != 1:
             raise ValueError(f"dataset {name}: only contiguous version-3 layouts are supported")
         addr, nbytes = struct.unpack_from("<QQ", layout, 2)
-        f.seek(addr)
-        g[name] = np.fromfile(f, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        g[name] = _Stored(f.name, addr, shape, dt)
     return g
