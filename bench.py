@@ -614,11 +614,20 @@ def bench_deck(ctx, name, args, headline):
             raise SystemExit(f"device-resident and host-pointer matvec disagree: {dev_err:.3e}")
         del xl_t, yl_t, xl, yl
 
+    huge = n * es > 8e9  # 42 spins: 25.6 GB per vector -- the solver needs the room the bench vectors take
+    def run_parity():
+        full = n <= 64_000_000 and headline
+        extra.update(parity_checks(ctx, cfg, basis, rd, n, np_dtype, xfull, ylocal, n_local, "full" if full else "windows",
+                                   args.parity_rows, f"{name} x{world}"))
+
+    if huge and not args.no_parity:  # the oracle checks need x and y: run them before the vectors are released
+        run_parity()
+
     # WARM time-to-ground-state: kernels already specialised, GPU clocks up (it follows the GPU legs
     # directly; the CPU-only oracle legs come afterwards); still includes the cache fill
     if not args.no_eigh:
         ffi.operatorSetCache(op, -1)  # drop the cache: time-to-ground-state includes building it
-        if n * es > 8e9:               # 42 spins: 25.6 GB per vector -- the solver needs the room
+        if huge:
             del xfull, xshard, ylocal
             xfull = None
         torch.cuda.empty_cache()
@@ -633,10 +642,8 @@ def bench_deck(ctx, name, args, headline):
         torch.cuda.empty_cache()
 
     # oracle checks at size (every world size): independent representatives + row-sample parity
-    if not args.no_parity and xfull is not None:
-        full = n <= 64_000_000 and headline
-        extra.update(parity_checks(ctx, cfg, basis, rd, n, np_dtype, xfull, ylocal, n_local, "full" if full else "windows",
-                                   args.parity_rows, f"{name} x{world}"))
+    if not args.no_parity and not huge:
+        run_parity()
 
     # CPU baseline (rank 0, one GPU only): the oracle port on the host cores, bounded row sample
     cpu_baseline = None

@@ -341,6 +341,7 @@ static u64 binom_host(int n, int k) {
 
 void Basis::build() {
   std::lock_guard<std::mutex> lock(mutex);
+  SPED_NVTX("sped: ls_build (enumerate representatives)");
   ensure_device_tables();
   auto t0 = std::chrono::steady_clock::now();
   Comm& cm = comm();
@@ -481,6 +482,7 @@ void Basis::build() {
 
 void Basis::adopt(u64 size, u64 const* reps_in) {
   std::lock_guard<std::mutex> lock(mutex);
+  SPED_NVTX("sped: ls_build_unsafe (adopt representatives)");
   ensure_device_tables();
   auto t0 = std::chrono::steady_clock::now();
   built = false;  // a failing ls_build_unsafe must not leave the previous basis marked as built
@@ -501,6 +503,7 @@ void Basis::adopt(u64 size, u64 const* reps_in) {
 }
 
 void Basis::finish_build() {
+  SPED_NVTX("sped: stabilisers + prefix buckets");
   index = BasisIndex{};
   index.n_states = n_states;
   if (trivial() && hamming_weight < 0) {

@@ -9,11 +9,16 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "internal.h"
 
 namespace sped {
 
 bool g_logging = std::getenv("SPED_LOG") != nullptr;  // also ls_enable_logging()
+
+NvtxRange::NvtxRange(char const* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 std::uint64_t g_launches = 0;
 
 static thread_local int t_last_code = 0;

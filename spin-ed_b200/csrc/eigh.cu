@@ -568,8 +568,11 @@ __global__ void __launch_bounds__(kThreads) copy_scaled_kernel(T const* src, u64
   (void)ldd;
 }
 
-// rows of V (n x m) <- rows * C (m x p), in place; C row-major in global memory
-template <class T>
+// rows of V (n x m) <- rows * C (m x p), in place; C row-major in global memory.  MAXM bounds m
+// at compile time so that the row lives in registers (a dynamically indexed 64-entry array would
+// sit in local memory: the restart of a 3-vector basis -- every iteration of the 40/42-spin decks --
+// then moves several times the bytes it has to).
+template <class T, int MAXM>
 __global__ void __launch_bounds__(kThreads) row_transform_kernel(T* V, u64 ld, int m, int p, double2 const* C, u64 n) {
   using A = typename VT<T>::Acc;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -577,11 +580,15 @@ __global__ void __launch_bounds__(kThreads) row_transform_kernel(T* V, u64 ld, i
   for (int j = threadIdx.x; j < m * p; j += blockDim.x) c[j] = C[j];
   __syncthreads();
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-    A row[kMaxBasis];
-    for (int j = 0; j < m; ++j) row[j] = VT<T>::load(V + (u64)j * ld + i);
+    A row[MAXM];
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j)
+      if (j < m) row[j] = VT<T>::load(V + (u64)j * ld + i);
     for (int q = 0; q < p; ++q) {
       A acc = from2<A>(make_double2(0, 0));
-      for (int j = 0; j < m; ++j) acc = addv(acc, mulc(row[j], c[j * p + q]));
+#pragma unroll
+      for (int j = 0; j < MAXM; ++j)
+        if (j < m) acc = addv(acc, mulc(row[j], c[j * p + q]));
       VT<T>::store(V + (u64)q * ld + i, acc);
     }
   }
@@ -742,6 +749,7 @@ struct Solver {
   // norms that decide whether a direction broke down (linearly dependent on the basis) are left
   // in d_norms[slot .. slot + nw) for the host to read with the next round trip.
   void ortho_block(int m, T* W, int nw, int slot) {
+    SPED_NVTX("sped_eigh: block orthogonalisation");
     CUDA_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(int), stream));
     ortho_sweep(m, W, nw, d_norms.ptr + slot, d_flag.ptr, nullptr);
     ortho_sweep(m, W, nw, nullptr, nullptr, d_flag.ptr);
@@ -770,6 +778,7 @@ struct Solver {
 
   // Wm[:, j0:j0+nb] = H V[:, j0:j0+nb]   (asynchronous)
   void apply(int j0, int nb) {
+    SPED_NVTX("sped_eigh: H V");
     Comm& cm = comm();
     if (!cm.active()) {
       op.matmat_device(dtype, nb, V.ptr + (u64)j0 * ld, ld, Wm.ptr + (u64)j0 * ld, ld, stream);
@@ -788,13 +797,21 @@ struct Solver {
     // (pageable source: the call returns once the data is staged, so `c` may go out of scope)
     CUDA_CHECK(cudaMemcpyAsync(transform_coeff.ptr, c.data(), c.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     size_t smem = c.size() * sizeof(double2);
-    if (smem > 48 * 1024)
-      CUDA_CHECK(cudaFuncSetAttribute(row_transform_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    row_transform_kernel<T><<<grid, kThreads, smem, stream>>>(M, ld, m, p, transform_coeff.ptr, n);
+    auto launch = [&](auto kernel) {
+      if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<grid, kThreads, smem, stream>>>(M, ld, m, p, transform_coeff.ptr, n);
+    };
+    if (m <= 4) launch(row_transform_kernel<T, 4>);
+    else if (m <= 8) launch(row_transform_kernel<T, 8>);
+    else if (m <= 16) launch(row_transform_kernel<T, 16>);
+    else if (m <= 32) launch(row_transform_kernel<T, 32>);
+    else launch(row_transform_kernel<T, kMaxBasis>);
     KERNEL_LAUNCHED();
   }
+
   int run(u64 k, double eps, int m_max, int b_max, int m_min, double* evals_out, void* evecs_out, double* rnorms_out,
           sped_monitor_fn monitor, void* mctx) {
+    SPED_NVTX("sped_eigh");
     double t_start = now_seconds();
     Basis& B = *op.basis;
     Comm& cm = comm();
@@ -850,6 +867,7 @@ struct Solver {
     // H[:, m_old:m_new) = V[:, 0:m_new)^H W[:, m_old:m_new), groups of kGroup columns per pass over V;
     // one device-to-host round trip for the whole block
     auto extend_projection = [&](int m_old, int m_new) {
+      SPED_NVTX("sped_eigh: projection V^H H V");
       int off = 0;
       for (int j0 = m_old; j0 < m_new; j0 += kGroup) {
         int const nw = std::min(kGroup, m_new - j0);
@@ -897,6 +915,7 @@ struct Solver {
       // residuals of ALL wanted pairs, kGroup per pass over V and W, one round trip for their norms
       bool const have_all = m >= (int)k;
       {
+        SPED_NVTX("sped_eigh: residuals");
         std::vector<double2> sblock;
         std::vector<double> th;
         int off = 0;
@@ -954,6 +973,7 @@ struct Solver {
       nb = (int)std::min<u64>((u64)nb, n_global - (u64)m);
       // restart when the new directions do not fit
       if (m + nb > mmax) {
+        SPED_NVTX("sped_eigh: restart");
         int r = std::min(std::max(keep, (int)std::min<u64>(k, (u64)m)), mmax - nb);
         r = std::max(r, 1);
         int p_room = mmax - nb - r;

@@ -26,6 +26,19 @@ namespace sped {
 
 extern bool g_logging;
 extern std::uint64_t g_launches;
+// NVTX ranges around the phases of the hot path (basis build, cache fill, matvec passes, exchange,
+// solver phases): visible in Nsight Systems / ncu --nvtx, free when no tool is attached (nvtx3 is
+// header-only and resolves its injection library lazily).
+struct NvtxRange {
+  explicit NvtxRange(char const* name);
+  ~NvtxRange();
+  NvtxRange(NvtxRange const&) = delete;
+  NvtxRange& operator=(NvtxRange const&) = delete;
+};
+#define SPED_NVTX_CAT2(a, b) a##b
+#define SPED_NVTX_CAT(a, b) SPED_NVTX_CAT2(a, b)
+#define SPED_NVTX(name) ::sped::NvtxRange SPED_NVTX_CAT(nvtx_range_, __LINE__)(name)
+
 #define SPED_LOG(...)                               \
   do {                                              \
     if (::sped::g_logging) {                        \

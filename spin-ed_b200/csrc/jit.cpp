@@ -12,8 +12,11 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <filesystem>
 #include <map>
 #include <sstream>
+#include <tuple>
 
 #include "internal.h"
 
@@ -34,6 +37,7 @@ struct NvrtcApi {
   nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
   nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
   nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  nvrtcResult (*Version)(int*, int*) = nullptr;
 };
 
 NvrtcApi& nvrtc() {
@@ -60,6 +64,7 @@ NvrtcApi& nvrtc() {
   a.GetProgramLogSize = reinterpret_cast<decltype(a.GetProgramLogSize)>(load("nvrtcGetProgramLogSize"));
   a.GetProgramLog = reinterpret_cast<decltype(a.GetProgramLog)>(load("nvrtcGetProgramLog"));
   a.DestroyProgram = reinterpret_cast<decltype(a.DestroyProgram)>(load("nvrtcDestroyProgram"));
+  a.Version = reinterpret_cast<decltype(a.Version)>(load("nvrtcVersion"));
   if (!ok) a.handle = nullptr;
   return a;
 }
@@ -269,15 +274,16 @@ struct Gen {
   }
 };
 
+// one loaded module = one kernel: the matrix-free matvec of a (dtype, columns) pair, or the cache fill
 struct Entry {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;
-  cudaKernel_t fill_kernel = nullptr;
   bool failed = false;
 };
+constexpr int kKindMatvec = 0, kKindFill = 1;
 
 struct Cache {
-  std::map<std::pair<int, int>, Entry> entries;
+  std::map<std::tuple<int, int, int>, Entry> entries;  // (kind, dtype, columns)
   ~Cache() {
     for (auto& e : entries)
       if (e.second.lib) cudaLibraryUnload(e.second.lib);
@@ -303,6 +309,12 @@ bool jit_enabled() {
 // NVRTC: generated program + matvec_kernel.cuh -> sm_100a cubin (empty on failure)
 // On-disk cache of compiled modules: $SPED_CACHE_DIR, else $XDG_CACHE_HOME/sped-b200, else
 // ~/.cache/sped-b200; the key hashes every source byte and option.  SPED_CACHE_DIR="" disables it.
+u64 fnv1a(void const* data, size_t n, u64 h = 0xcbf29ce484222325ull) {
+  auto p = static_cast<unsigned char const*>(data);
+  for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+  return h;
+}
+
 std::string cubin_cache_path(std::string const& header) {
   char const* dir = std::getenv("SPED_CACHE_DIR");
   std::string base;
@@ -316,41 +328,70 @@ std::string cubin_cache_path(std::string const& header) {
   } else {
     return "";
   }
-  u64 h = 0xcbf29ce484222325ull;
-  auto mix = [&](char const* s) {
-    for (; *s; ++s) h = (h ^ (unsigned char)*s) * 0x100000001b3ull;
-    h = (h ^ 0xff) * 0x100000001b3ull;
-  };
-  mix(header.c_str());
-  mix(k_src_device_types);
-  mix(k_src_matvec_kernel);
-  mix("sm_100a c++17 lineinfo v1");
-  std::string mk = "mkdir -p '" + base + "' 2>/dev/null";
-  if (std::system(mk.c_str()) != 0) return "";
+  // the key covers every source byte, every option and the compiler that would produce the module
+  int major = 0, minor = 0;
+  NvrtcApi& api = nvrtc();
+  if (api.handle && api.Version) api.Version(&major, &minor);
+  std::string const options = "sm_100a c++17 lineinfo v2 nvrtc " + std::to_string(major) + "." + std::to_string(minor);
+  u64 h = fnv1a(header.data(), header.size());
+  h = fnv1a(k_src_device_types, std::strlen(k_src_device_types), h ^ 0xff);
+  h = fnv1a(k_src_matvec_kernel, std::strlen(k_src_matvec_kernel), h ^ 0xff);
+  h = fnv1a(options.data(), options.size(), h ^ 0xff);
+  std::error_code ec;  // no shell, no fork: the process may hold CUDA and NCCL state
+  std::filesystem::create_directories(base, ec);
+  if (ec) return "";
   char name[32];
   std::snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
   return base + name;
 }
 
-std::vector<char> compile_cubin(Basis& b, int dtype, int nb) {
+// cache file = "SPEDCUB2" | payload size | FNV-1a of the payload | payload; anything else is ignored
+constexpr char kCacheMagic[8] = {'S', 'P', 'E', 'D', 'C', 'U', 'B', '2'};
+
+std::vector<char> read_cached_cubin(std::string const& path) {
+  std::vector<char> cubin;
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return cubin;
+  char magic[8];
+  u64 size = 0, sum = 0;
+  bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, kCacheMagic, 8) == 0 && std::fread(&size, 8, 1, f) == 1 &&
+            std::fread(&sum, 8, 1, f) == 1 && size > 0 && size < ((u64)1 << 31);
+  if (ok) {
+    cubin.resize((size_t)size);
+    ok = std::fread(cubin.data(), 1, cubin.size(), f) == cubin.size() && std::fgetc(f) == EOF &&
+         fnv1a(cubin.data(), cubin.size()) == sum;
+  }
+  std::fclose(f);
+  if (!ok) {
+    cubin.clear();
+    SPED_LOG("jit: ignoring damaged or foreign cache entry %s", path.c_str());
+  }
+  return cubin;
+}
+
+void write_cached_cubin(std::string const& path, std::vector<char> const& cubin) {
+  // published atomically: several ranks may compile the same module at the same time
+  std::string tmp = path + "." + std::to_string((long)getpid()) + ".tmp";
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  u64 const size = cubin.size(), sum = fnv1a(cubin.data(), cubin.size());
+  bool ok = std::fwrite(kCacheMagic, 1, 8, f) == 8 && std::fwrite(&size, 8, 1, f) == 1 && std::fwrite(&sum, 8, 1, f) == 1 &&
+            std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+
+std::vector<char> compile_cubin(Basis& b, int kind, int dtype, int nb) {
   std::vector<char> cubin;
   std::string program = Gen(b.program).run();
-  std::string header = std::string("#define SPED_T ") + dtype_name(dtype) + "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
+  std::string header = std::string("#define SPED_JIT_KIND ") + std::to_string(kind) + "\n#define SPED_T " + dtype_name(dtype) +
+                       "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
   std::string cache_file = cubin_cache_path(header);
   if (!cache_file.empty()) {
-    if (FILE* f = std::fopen(cache_file.c_str(), "rb")) {
-      std::fseek(f, 0, SEEK_END);
-      long size = std::ftell(f);
-      std::fseek(f, 0, SEEK_SET);
-      if (size > 0) {
-        cubin.resize((size_t)size);
-        if (std::fread(cubin.data(), 1, cubin.size(), f) != cubin.size()) cubin.clear();
-      }
-      std::fclose(f);
-      if (!cubin.empty()) {
-        SPED_LOG("jit: reusing %s", cache_file.c_str());
-        return cubin;
-      }
+    cubin = read_cached_cubin(cache_file);
+    if (!cubin.empty()) {
+      SPED_LOG("jit: reusing %s", cache_file.c_str());
+      return cubin;
     }
   }
   NvrtcApi& api = nvrtc();
@@ -382,14 +423,7 @@ std::vector<char> compile_cubin(Basis& b, int dtype, int nb) {
   cubin.resize(size);
   api.GetCUBIN(prog, cubin.data());
   api.DestroyProgram(&prog);
-  if (!cache_file.empty()) {  // publish atomically: several ranks may compile the same module
-    std::string tmp = cache_file + "." + std::to_string((long)getpid()) + ".tmp";
-    if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
-      bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
-      ok = (std::fclose(f) == 0) && ok;
-      if (!ok || std::rename(tmp.c_str(), cache_file.c_str()) != 0) std::remove(tmp.c_str());
-    }
-  }
+  if (!cache_file.empty()) write_cached_cubin(cache_file, cubin);
   if (char const* dump = std::getenv("SPED_JIT_DUMP")) {  // inspection: cuobjdump -sass <file>
     if (FILE* f = std::fopen(dump, "wb")) {
       std::fwrite(cubin.data(), 1, cubin.size(), f);
@@ -399,18 +433,17 @@ std::vector<char> compile_cubin(Basis& b, int dtype, int nb) {
   return cubin;
 }
 
-Entry compile(Basis& b, int dtype, int nb) {
+Entry compile(Basis& b, int kind, int dtype, int nb) {
   Entry out;
   auto t0 = std::chrono::steady_clock::now();
-  std::vector<char> cubin = compile_cubin(b, dtype, nb);
+  std::vector<char> cubin = compile_cubin(b, kind, dtype, nb);
   size_t size = cubin.size();
   if (cubin.empty()) {
     out.failed = true;
     return out;
   }
   cudaError_t e = cudaLibraryLoadData(&out.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-  if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.kernel, out.lib, "sped_matvec_jit");
-  if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.fill_kernel, out.lib, "sped_cache_fill_jit");
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.kernel, out.lib, kind == kKindFill ? "sped_cache_fill_jit" : "sped_matvec_jit");
   if (e != cudaSuccess) {
     std::fprintf(stderr, "[sped] jit: loading the specialised kernel failed (%s), using the interpreted-program kernel\n",
                  cudaGetErrorString(e));
@@ -420,40 +453,38 @@ Entry compile(Basis& b, int dtype, int nb) {
     return out;
   }
   double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  SPED_LOG("jit: specialised matvec (%s, %d columns, %zu steps) compiled in %.2f s, cubin %zu bytes", dtype_name(dtype), nb,
-           b.program.steps.size(), dt, size);
+  SPED_LOG("jit: specialised %s (%s, %d columns, %zu steps) ready in %.2f s, cubin %zu bytes",
+           kind == kKindFill ? "cache fill" : "matvec", dtype_name(dtype), nb, b.program.steps.size(), dt, size);
   return out;
+}
+
+void* jit_kernel(Basis& b, int kind, int dtype, int nb) {
+  if (!jit_enabled() || b.trivial()) return nullptr;
+  std::lock_guard<std::mutex> lock(g_jit_mutex);
+  if (!b.jit_cache) b.jit_cache = std::make_shared<Cache>();
+  Cache& c = *static_cast<Cache*>(b.jit_cache.get());
+  auto key = std::make_tuple(kind, dtype, nb);
+  auto it = c.entries.find(key);
+  if (it == c.entries.end()) it = c.entries.emplace(key, compile(b, kind, dtype, nb)).first;
+  return it->second.failed ? nullptr : (void*)it->second.kernel;
 }
 
 }  // namespace
 
 size_t jit_compile_only(Basis& b, int dtype, int nb) {
-  std::vector<char> cubin = compile_cubin(b, dtype, nb);
+  std::vector<char> cubin = compile_cubin(b, kKindMatvec, dtype, nb);
   if (cubin.empty()) fail(SPED_INTERNAL_ERROR, "NVRTC compilation of the specialised kernel failed");
+  std::vector<char> fill = compile_cubin(b, kKindFill, SPED_F64, 1);
+  if (fill.empty()) fail(SPED_INTERNAL_ERROR, "NVRTC compilation of the specialised cache-fill kernel failed");
   return cubin.size();
 }
 
 // Source of the specialised canonicalisation (exposed for tests and inspection).
 std::string jit_program_source(Basis const& b) { return Gen(b.program).run(); }
 
-void* jit_matvec_kernel(Basis& b, int dtype, int nb) {
-  if (!jit_enabled() || b.trivial()) return nullptr;
-  std::lock_guard<std::mutex> lock(g_jit_mutex);
-  if (!b.jit_cache) b.jit_cache = std::make_shared<Cache>();
-  Cache& c = *static_cast<Cache*>(b.jit_cache.get());
-  auto key = std::make_pair(dtype, nb);
-  auto it = c.entries.find(key);
-  if (it == c.entries.end()) it = c.entries.emplace(key, compile(b, dtype, nb)).first;
-  return it->second.failed ? nullptr : (void*)it->second.kernel;
-}
+void* jit_matvec_kernel(Basis& b, int dtype, int nb) { return jit_kernel(b, kKindMatvec, dtype, nb); }
 
-// The cache-fill entry point lives in every specialised module; use (or build) the f64 one.
-void* jit_cache_fill_kernel(Basis& b) {
-  if (!jit_matvec_kernel(b, SPED_F64, 1)) return nullptr;
-  std::lock_guard<std::mutex> lock(g_jit_mutex);
-  Cache& c = *static_cast<Cache*>(b.jit_cache.get());
-  auto it = c.entries.find(std::make_pair((int)SPED_F64, 1));
-  return (it == c.entries.end() || it->second.failed) ? nullptr : (void*)it->second.fill_kernel;
-}
+// The cache fill does not depend on the storage type: one module per basis.
+void* jit_cache_fill_kernel(Basis& b) { return jit_kernel(b, kKindFill, SPED_F64, 1); }
 
 }  // namespace sped

@@ -288,17 +288,22 @@ struct JitCanon {
   __device__ __forceinline__ void operator()(u64 x, u64& rep, int& phase) const { sped_jit_canonicalize(x, rep, phase); }
 };
 
+// One entry point per module (SPED_JIT_KIND: 0 matvec, 1 cache fill): the generated canonicalisation
+// is thousands of lines of straight-line code, and compiling it into a kernel that the run never
+// launches would double the NVRTC time of the first (cold) solve.
+#if SPED_JIT_KIND == 0
 extern "C" __global__ void __launch_bounds__(256) sped_matvec_jit(MatvecParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<Traits<SPED_T>::cplx>(p.terms, smem);
   matvec_rows<SPED_T, SPED_NB>(p, terms, JitCanon());
 }
-
+#else
 extern "C" __global__ void __launch_bounds__(256) sped_cache_fill_jit(FillParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   TermsView terms = stage_terms<false>(p.terms, smem);
   cache_fill_rows(p, terms, JitCanon());
 }
+#endif
 #endif
 
 }  // namespace sped

@@ -373,6 +373,7 @@ bool Operator::cache_usable() {
   u64 const n_local = dist.n_local;
   if (n_local == 0) return false;
   auto t0 = std::chrono::steady_clock::now();
+  SPED_NVTX("sped: operator cache fill (matrix-free traversal)");
 
   CodeMaps cm_;
   if (char const* why = build_code_maps(*this, cm_)) return reject(why);
@@ -515,6 +516,7 @@ void Operator::cached_count(unsigned long long* d_out) {
 
 void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s, u64 row_lo,
                              u64 row_hi, int phase, bool beside_transfer) {
+  SPED_NVTX(phase == 0 ? "sped: cached matvec (all classes)" : phase == 1 ? "sped: cached matvec (local class)" : "sped: cached matvec (remote class)");
   static bool const fetch_set = [] {  // tuning knob: DRAM->L2 fetch granularity (32, 64 or 128 bytes)
     char const* e = std::getenv("SPED_L2_FETCH");
     if (e && *e) {

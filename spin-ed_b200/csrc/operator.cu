@@ -367,6 +367,7 @@ static MatvecParams make_params(Operator& op) {
 }
 
 void Operator::matmat_device(int dtype, u64 block, void const* x, u64 xs, void* y, u64 ys, cudaStream_t s) {
+  SPED_NVTX("sped: matmat (device buffers)");
   prepare();
   if (!dtype_is_complex(dtype) && !is_real()) fail(LS_OPERATOR_IS_COMPLEX, "operator is complex but a real datatype was requested");
   if (block == 0 || dist.n_local == 0) return;
@@ -402,6 +403,7 @@ void packed_terms_host(std::vector<Interaction> const& terms, std::vector<DevBon
 // streaming kernel already handles the elements whose source entries this rank owns; the remote
 // class follows once the gather has landed.  (Matrix-free mode: gather, then one kernel.)
 void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, void* xfull, cudaStream_t s) {
+  SPED_NVTX("sped: sharded matvec (exchange + class passes)");
   prepare();
   Comm& cm = comm();
   size_t const es = dtype_size(dtype);
@@ -575,6 +577,7 @@ void convert_layout(bool to_dist, size_t es, void const* src, void* dst, RowDist
 // Host-pointer entry (the reference's PRIMME callback shape): stage x to the device, apply, copy
 // back.  With several ranks every rank passes the full x and receives the full y.
 void Operator::matmat_host(int dtype, u64 size, u64 block, void const* x, u64 xs, void* y, u64 ys) {
+  SPED_NVTX("sped: ls_operator_matmat (host buffers)");
   prepare();
   Basis& b = *basis;
   if (size != b.n_states) fail(LS_DIMENSION_MISMATCH, "size does not match the number of representatives");
@@ -701,6 +704,7 @@ static void launch_dot(void const* x, void const* y, u64 n, double2* partial, in
 }
 
 void Operator::expectation_host(int dtype, u64 size, u64 block, void const* x, u64 xs, cplx* out) {
+  SPED_NVTX("sped: ls_operator_expectation");
   prepare();
   Basis& b = *basis;
   if (size != b.n_states) fail(LS_DIMENSION_MISMATCH, "size does not match the number of representatives");
