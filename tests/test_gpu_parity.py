@@ -377,3 +377,24 @@ def test_xxz_triangular_19_eigenvectors_are_orthonormal_eigenvectors(oracle):
         assert np.linalg.norm(hv[:, i] - ev[i] * vecs[:, i]) <= 2e-6 * a_norm, (i, ev)
     assert abs(ev[0] + 8.6351360078) < 1e-6
     print("xxz_triangular_19 lowest six:", ev)
+
+
+@pytest.mark.parametrize("n", [16, 24])
+def test_ground_state_energy_agrees_between_sector_descriptions(n):
+    """Size-independent check used at 36-42 spins (tools/sector_cross_check.py): the fully symmetric
+    sector (translations x parity x spin inversion) and the larger translations-only sector share
+    nothing but the physics -- different group, representatives, norms, basis size -- yet hold the
+    same ground state, so E0 must agree to 1e-10 relative."""
+    full = decks.chain(n, n // 2, 1, (0, 0))
+    larger = decks.chain(n, n // 2, 1, (0, 0))
+    larger["basis"]["symmetries"] = larger["basis"]["symmetries"][:1]
+    e0, dims = [], []
+    for cfg in (full, larger):
+        uc = product_problem(cfg)
+        ffi.buildBasis(uc.cBasis)
+        dims.append(ffi.getNumberStates(uc.cBasis))
+        ev, _, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 1, want_vectors=False)
+        assert rn[0] <= 1e-8 * max(1.0, abs(ev[0]))
+        e0.append(ev[0])
+    assert dims[1] > 1.5 * dims[0]
+    assert abs(e0[0] - e0[1]) <= 1e-10 * abs(e0[0]), (e0, dims)
