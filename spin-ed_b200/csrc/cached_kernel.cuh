@@ -29,6 +29,7 @@ struct CachedParams {
   u64 row_lo, row_hi;  // local rows handled by this launch (row_lo is a multiple of 32)
   int beside_transfer; // this pass overlaps an exchange round (see launch_cached_kernel)
   int phase;           // kPhaseAll, or 1 + class (CacheView): class 0 starts from the diagonal, later classes add to y
+  float mean_row_length;  // slots per local row (host side: picks the batch length of the streaming kernel)
 };
 constexpr int kPhaseAll = 0;     // diagonal + every stored element
 constexpr int kPhaseLocal = 1;   // diagonal + elements whose source this rank owns (needs no exchange); 2, 3: exchange rounds
@@ -267,7 +268,7 @@ __device__ __forceinline__ void acc_add(double2& a, double2 x) { a.x += x.x; a.y
 // ones (back of the region, downwards; each looks its coefficient up).  Elements are taken U at a
 // time: all U index loads are issued first, then the U gathers, then the U accumulations in order,
 // so every thread keeps U independent gathers in flight.
-template <class T, int NB, class Code, bool SYM, bool HINT, int U, int MINB>
+template <class T, int NB, class Code, bool SYM, bool HINT, int U, int MINB, bool PIPE = false>
 SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Traits<T>::cplx ? 1 : MINB) cached_matvec_kernel(CachedParams p) {
   typedef Traits<T> TR;
   typedef typename TR::Acc Acc;
@@ -327,16 +328,38 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Trait
       if (nd) {
         Acc part = acc_zero(Acc());
         u32 const* q = cidx + slice_base + (u64)lo * 32;
-#pragma unroll 1
-        for (u32 j0 = 0; j0 < nd; j0 += U, q += 32 * U) {
+        if constexpr (PIPE) {
+          // software pipeline: the positions of the NEXT batch are requested right behind the gathers of
+          // the current one, so their latency hides behind the gathers instead of preceding them
           u32 idx[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) idx[u] = load_stream_if<HINT>(j0 + u < nd, q + 32 * u, pol_stream);
-          Acc xv[U];
+          for (int u = 0; u < U; ++u) idx[u] = load_stream_if<HINT>((u32)u < nd, q + 32 * u, pol_stream);
+#pragma unroll 1
+          for (u32 j0 = 0; j0 < nd; j0 += U) {
+            Acc xv[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) xv[u] = load_x_if<HINT>(j0 + u < nd, x + idx[u], pol_x);  // dead slots: no request, zero
+            for (int u = 0; u < U; ++u) xv[u] = load_x_if<HINT>(j0 + u < nd, x + idx[u], pol_x);
+            q += 32 * U;
+            u32 nxt[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) acc_add(part, xv[u]);
+            for (int u = 0; u < U; ++u) nxt[u] = load_stream_if<HINT>(j0 + U + u < nd, q + 32 * u, pol_stream);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc_add(part, xv[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) idx[u] = nxt[u];
+          }
+        } else {
+#pragma unroll 1
+          for (u32 j0 = 0; j0 < nd; j0 += U, q += 32 * U) {
+            u32 idx[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) idx[u] = load_stream_if<HINT>(j0 + u < nd, q + 32 * u, pol_stream);
+            Acc xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = load_x_if<HINT>(j0 + u < nd, x + idx[u], pol_x);  // dead slots: no request, zero
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc_add(part, xv[u]);
+          }
         }
         acc_fma(acc, w_default, part);
       }

@@ -259,15 +259,35 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   cp.sym = pr.sym ? 1 : 0;
   cp.row_lo = 0;
   cp.row_hi = n_local;
+  // one pass over all classes: the pipelined batch-of-8 kernel; class by class: the pipelined batch-of-6
+  // kernel (the two the product launches, with plain loads); a third, unpipelined run checks the plain loop
   auto launch = [&](T* y, int phase) {
     cp.y = y;
     cp.phase = phase;
-    if (wide && pr.sym) cached_matvec_kernel<T, 1, std::uint16_t, true, false, 4, 6>(cp);
-    else if (wide) cached_matvec_kernel<T, 1, std::uint16_t, false, false, 4, 6>(cp);
-    else if (pr.sym) cached_matvec_kernel<T, 1, std::uint8_t, true, false, 4, 6>(cp);
-    else cached_matvec_kernel<T, 1, std::uint8_t, false, false, 4, 6>(cp);
+    auto go = [&](auto code_tag, auto sym_tag) {
+      using Code = decltype(code_tag);
+      constexpr bool S = decltype(sym_tag)::value;
+      if (phase == 0) cached_matvec_kernel<T, 1, Code, S, false, 8, 4, true>(cp);
+      else cached_matvec_kernel<T, 1, Code, S, false, 6, 4, true>(cp);
+    };
+    if (wide && pr.sym) go(std::uint16_t{}, std::true_type{});
+    else if (wide) go(std::uint16_t{}, std::false_type{});
+    else if (pr.sym) go(std::uint8_t{}, std::true_type{});
+    else go(std::uint8_t{}, std::false_type{});
   };
   if (n_local) {
+    {  // the unpipelined loop must give the same sums (same order): checked here, bit for bit
+      std::vector<T> plain(n_local);
+      cp.y = plain.data();
+      cp.phase = 0;
+      if (wide && pr.sym) cached_matvec_kernel<T, 1, std::uint16_t, true, false, 4, 6, false>(cp);
+      else if (wide) cached_matvec_kernel<T, 1, std::uint16_t, false, false, 4, 6, false>(cp);
+      else if (pr.sym) cached_matvec_kernel<T, 1, std::uint8_t, true, false, 4, 6, false>(cp);
+      else cached_matvec_kernel<T, 1, std::uint8_t, false, false, 4, 6, false>(cp);
+      launch(y_all, 0);
+      if (std::memcmp(plain.data(), y_all, n_local * sizeof(T)) != 0)
+        fail(SPED_INTERNAL_ERROR, "emulation: pipelined and plain streaming loops disagree");
+    }
     launch(y_all, 0);
     for (u32 ph = 1; ph <= 1 + rounds; ++ph) launch(y_phased, (int)ph);  // local pass, then one pass per exchange round
   }

@@ -143,12 +143,12 @@ __global__ void table_kernel(double const* values_re, double const* values_im, d
 namespace sped {
 namespace {
 
-// SPED_CACHED_VARIANT (tuning knob, default = the measured best): bit 0 cache-policy loads; bits 1..3
-// elements in flight per thread / resident blocks per SM the register budget is set for.
+// SPED_CACHED_VARIANT (tuning knob; unset = the measured best, chosen by row length): 0 plain loads,
+// 19 / 33 the two default kernels, other values only in builds with -DSPED_CACHED_SWEEP.
 int cached_variant() {
   static int v = [] {
     char const* e = std::getenv("SPED_CACHED_VARIANT");
-    return e && *e ? std::atoi(e) : 1;
+    return e && *e ? std::atoi(e) : -1;
   }();
   return v;
 }
@@ -175,15 +175,29 @@ template <class T, int NB, class Code, bool SYM>
 void launch_cached_variant(CachedParams const& p, cudaStream_t s) {
   switch (cached_variant()) {
     case 0: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, false, 4, 6>>(p, s); break;
-#if defined(SPED_CACHED_SWEEP)  // tuning builds only (tools/sweep_cached.sh): (elements in flight, blocks per SM)
+#if defined(SPED_CACHED_SWEEP)  // tuning builds only (profiles/r02_kernel_variants.md): (elements in flight, blocks per SM[, pipelined])
     case 3: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 5>>(p, s); break;
     case 5: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 8>>(p, s); break;
     case 7: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 2, 8>>(p, s); break;
     case 9: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 6>>(p, s); break;
-    case 11: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 3, 7>>(p, s); break;
-    case 13: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 7>>(p, s); break;
+    case 11: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 6, 5>>(p, s); break;
+    case 15: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 6, 5, true>>(p, s); break;
+    case 17: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 6, true>>(p, s); break;
+    case 23: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 4, 5, true>>(p, s); break;
+    case 25: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 5, true>>(p, s); break;
+    case 27: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 10, 4, true>>(p, s); break;
+    case 29: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 12, 3, true>>(p, s); break;
+    case 31: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 3, true>>(p, s); break;
+    case 35: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 4, false>>(p, s); break;
 #endif
-    default: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 6, 5>>(p, s); break;
+    case 19: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 4, true>>(p, s); break;
+    case 33: launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 6, 4, true>>(p, s); break;
+    default:
+      // software-pipelined position loads, 4 blocks of 256 per SM (64 registers); batches of 6 for long
+      // rows (6x6: 37 elements per row, 1.31 ms), of 8 for short ones (chain_36: 18.5, 2.57 ms) -- measured
+      if (p.mean_row_length >= 28.0f) launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 6, 4, true>>(p, s);
+      else launch_cached_kernel<cached_matvec_kernel<T, NB, Code, SYM, true, 8, 4, true>>(p, s);
+      break;
   }
 }
 
@@ -535,6 +549,7 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
                       c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_rounds};
   p.phase = phase;
   p.beside_transfer = beside_transfer ? 1 : 0;
+  p.mean_row_length = dist.n_local ? (float)((double)c_slots / (double)dist.n_local) : 0.0f;
   p.ctx = mp.ctx;
   p.diag_re = mp.diag_re;
   p.diag_im = mp.diag_im;
