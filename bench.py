@@ -392,9 +392,10 @@ def parity_checks(ctx, cfg, basis, rd, n, np_dtype, xfull, ylocal, n_local, inde
     return out
 
 
-def bench_deck(ctx, name, args, headline):
+def bench_deck(ctx, name, args, headline, solves="both"):
     """Everything measured on one deck.  headline: the full set of legs (block applications, f32
-    storage, host-buffer e2e, CPU baseline); otherwise the sharded-size subset."""
+    storage, host-buffer e2e, CPU baseline); otherwise the sharded-size subset.  solves: "both" -- a
+    cold and a warm time-to-ground-state; "cold" -- the first (cold) solve only."""
     torch, dist, ffi = ctx.torch, ctx.dist, ctx.ffi
     from spin_ed_b200 import config as sconfig
     from spin_ed_b200 import decks
@@ -436,10 +437,17 @@ def bench_deck(ctx, name, args, headline):
     # (0) COLD time-to-ground-state: first use of this operator in the process -- includes the NVRTC
     #     specialisation of the canonicalisation (unless its cubin is in the disk cache), the
     #     matrix-free traversal that fills the operator cache, and the solve
+    # a shard of more than 4 GB per vector (chain_40 on ONE GPU: 6.9 GB) leaves no room for the cache's
+    # automatic "keep space for a solver" reserve beside the bench vectors: ask for the cache outright
+    cache_mode = 1 if n_local * es > 4e9 else -1
     if not args.no_eigh:
         dt, evals, rnorms, st = solve("cold")
         extra.update({"time_to_ground_state_cold_s": dt, "eigenvalues": evals, "residual_norms": rnorms,
                       "cold_includes": "NVRTC compile of the specialised kernels + operator-cache fill + solve"})
+        if solves == "cold":
+            extra.update({"time_to_ground_state_s": dt, "eigh_matvecs": st["matvecs"], "eigh_restarts": st["restarts"],
+                          "eigh_seconds_matvec": st["seconds_matvec"], "eigh_stats": st,
+                          "eigh_dtype": "f64 (deck asks " + spec.datatype + ")", "warm_solve": "not run (one solve only)"})
         if n * es > 2e9:  # 40/42 spins: the solver's workspace (tens of GB) must not sit beside the bench vectors
             ffi.operatorReleaseWorkspace(op)
         torch.cuda.empty_cache()
@@ -492,7 +500,8 @@ def bench_deck(ctx, name, args, headline):
     ctx.barrier()
     matrix_free_ms = ctx.allmax(timed(step, max(2, min(args.steps, 3))))
     # (b) the default path: elements cached in HBM by the first application (if they fit)
-    ffi.operatorSetCache(op, -1)
+    torch.cuda.empty_cache()
+    ffi.operatorSetCache(op, cache_mode)
     for _ in range(args.warmup):
         step()
     ctx.barrier()
@@ -625,7 +634,7 @@ def bench_deck(ctx, name, args, headline):
 
     # WARM time-to-ground-state: kernels already specialised, GPU clocks up (it follows the GPU legs
     # directly; the CPU-only oracle legs come afterwards); still includes the cache fill
-    if not args.no_eigh:
+    if not args.no_eigh and solves == "both":
         ffi.operatorSetCache(op, -1)  # drop the cache: time-to-ground-state includes building it
         if huge:
             del xfull, xshard, ylocal
@@ -683,11 +692,12 @@ def run_ours(args):
     world, rank = ctx.world, ctx.rank
     r = bench_deck(ctx, args.config, args, headline=True)
     extra = r["extra"]
-    # the sharded north-star deck beside the headline one whenever there is more than one GPU
-    # (BASELINE.json: heisenberg_chain_40 over 2/4/8 B200); step-time roofline fraction included
+    # the sharded north-star deck beside the headline one (BASELINE.json: heisenberg_chain_40 over
+    # 1/2/4/8 B200); step-time roofline fraction included.  On ONE GPU its operator cache (80 GB) and
+    # a 3-vector solver just fit: one (cold) solve only, to keep the default run within minutes.
     sharded = {}
-    if world > 1 and args.sharded_deck and args.sharded_deck != args.config:
-        s = bench_deck(ctx, args.sharded_deck, args, headline=False)
+    if args.sharded_deck and args.sharded_deck != args.config and (world > 1 or not args.no_sharded_at_one):
+        s = bench_deck(ctx, args.sharded_deck, args, headline=False, solves="both" if world > 1 else "cold")
         sx = s["extra"]
         sharded = {
             "workload": s["name"], "rows": s["rows"], "offdiag_elements": s["n_off"], "ms_per_step": s["ms_per_step"],
@@ -749,6 +759,7 @@ def main():
     ap.add_argument("--e2e-host-gb", type=float, default=24.0, help="skip the host-buffer leg above this much pinned memory")
     ap.add_argument("--watchdog-seconds", type=float, default=1500.0,
                     help="abort the process if the whole run takes longer (a mismatched collective hangs every rank)")
+    ap.add_argument("--no-sharded-at-one", action="store_true", help="one GPU: skip the sharded deck (chain_40 takes ~1.5 min there)")
     ap.add_argument("--no-eigh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

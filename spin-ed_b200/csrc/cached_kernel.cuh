@@ -366,15 +366,15 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, Trait
       // coded: element j at slot hi - 1 - j
       if (nx) {
         u64 const top = slice_base + (u64)(hi - 1u) * 32;
+        u64 const cbase = __ldg(p.cache.code_off + slice * p.cache.n_classes + cls) + (i & 31);  // compact code stream
 #pragma unroll 1
         for (u32 j0 = 0; j0 < nx; j0 += U) {
           u32 idx[U], code[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             bool const live = j0 + u < nx;
-            u64 const pos = top - (u64)(j0 + u) * 32;
-            idx[u] = load_stream_if<HINT>(live, cidx + pos, pol_stream);
-            code[u] = load_stream_if<HINT>(live, ccode + pos, pol_stream);
+            idx[u] = load_stream_if<HINT>(live, cidx + (top - (u64)(j0 + u) * 32), pol_stream);
+            code[u] = load_stream_if<HINT>(live, ccode + (cbase + (u64)(j0 + u) * 32), pol_stream);
           }
           Acc xv[U];
 #pragma unroll
@@ -589,17 +589,17 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, (size
 #pragma unroll
         for (int c = 0; c < NB; ++c) acc_fma(acc[c], w_default, part[c]);
       }
-      if (nx) {  // coded: element j at slot hi - 1 - j
+      if (nx) {  // coded: element j at slot hi - 1 - j, its code at entry j of the compact code stream
         u64 const top = slice_base + (u64)(hi - 1u) * 32;
+        u64 const cbase = __ldg(p.cache.code_off + slice * p.cache.n_classes + cls) + (i & 31);
 #pragma unroll 1
         for (u32 j0 = 0; j0 < nx; j0 += U) {
           u32 idx[U], code[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             bool const live = j0 + u < nx;
-            u64 const pos = top - (u64)(j0 + u) * 32;
-            idx[u] = load_stream_if<kBlockHint>(live, cidx + pos, pol_stream);
-            code[u] = load_stream_if<kBlockHint>(live, ccode + pos, pol_stream);
+            idx[u] = load_stream_if<kBlockHint>(live, cidx + (top - (u64)(j0 + u) * 32), pol_stream);
+            code[u] = load_stream_if<kBlockHint>(live, ccode + (cbase + (u64)(j0 + u) * 32), pol_stream);
           }
           Acc xv[U][NB];
 #pragma unroll
@@ -616,6 +616,51 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS, (size
 #pragma unroll
     for (int c = 0; c < NB; ++c)
       if (c < (int)p.ncols) TR::store(y + (u64)c * p.ys + i, acc[c]);
+  }
+}
+
+// ---- compact code stream --------------------------------------------------------------------
+// The fill writes the code of a coded element beside its position (one code per slot, a temporary);
+// afterwards only the coded parts are kept: class c of slice s gets cw = max over its lanes of the
+// coded elements, and entry j of lane l lives at code_off[s * n_classes + c] + 32 j + l.
+
+// cw[s * n_classes + c] = longest coded list of class c among the lanes of slice s (one thread per
+// slice), for the slices slice_lo .. slice_hi - 1
+SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) code_width_kernel(dev_u16 const* len, u64 n_local, u32 n_classes,
+                                                                                             u64 slice_lo, u64 slice_hi, u32* cw) {
+  for (u64 s = slice_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; s < slice_hi; s += (u64)gridDim.x * blockDim.x) {
+    u64 const hi = (32 * s + 32 < n_local) ? 32 * s + 32 : n_local;
+    for (u32 c = 0; c < n_classes; ++c) {
+      u32 mx = 0;
+      for (u64 i = 32 * s; i < hi; ++i) {
+        u32 const v = __ldg(len + (u64)(2 * c + 1) * n_local + i);
+        mx = v > mx ? v : mx;
+      }
+      cw[s * n_classes + c] = mx;
+    }
+  }
+}
+
+// The codes of the coded elements of the local rows row_lo .. row_hi - 1 in compact order.  `c.code`
+// still is the one-per-slot temporary of the fill, which covers the slots from code_slot0 on;
+// `chunk_off` holds the offsets of this chunk's regions relative to `out`:
+// chunk_off[(s - row_lo / 32) * n_classes + cls].
+template <class Code>
+SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) code_compact_kernel(CacheView c, u64 n_local, u64 row_lo, u64 row_hi,
+                                                                                               u64 code_slot0, u64 const* chunk_off, Code* out) {
+  Code const* __restrict__ full = static_cast<Code const*>(c.code);
+  for (u64 i = row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < row_hi; i += (u64)gridDim.x * blockDim.x) {
+    u64 const slice = i >> 5;
+    u64 const slice_base = __ldg(c.slice_off + slice) + (i & 31);
+    u32 const width = (u32)((__ldg(c.slice_off + slice + 1) - __ldg(c.slice_off + slice)) >> 5);
+    for (u32 cls = 0; cls < c.n_classes; ++cls) {
+      u32 const nx = __ldg(c.len + (u64)(2 * cls + 1) * n_local + i);
+      if (!nx) continue;
+      u32 const hi = cls + 1 == c.n_classes ? width : __ldg(c.slice_start + kClassStride * slice + cls);
+      u64 const top = slice_base + (u64)(hi - 1u) * 32 - code_slot0;
+      u64 const cbase = __ldg(chunk_off + (slice - (row_lo >> 5)) * c.n_classes + cls) + (i & 31);
+      for (u32 j = 0; j < nx; ++j) out[cbase + (u64)j * 32] = full[top - (u64)j * 32];
+    }
   }
 }
 

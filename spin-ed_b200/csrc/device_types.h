@@ -120,7 +120,8 @@ constexpr int kClassStride = kMaxClasses - 1;  // slice_start entries per slice
 struct CacheView {
   u64 const* slice_off;  // [n_slices + 1], in elements
   u32 const* idx;        // position of the target in the replicated vector ([rank][local] layout)
-  void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16
+  void const* code;      // index into `table`: u8 when there are <= 256 codes, else u16; COMPACT: only the
+                         // coded elements have an entry, see code_off
   dev_u16 const* len;    // [2 * n_classes][local rows]: per source class the elements that carry the
                          // default coefficient (no code is read for them), then the coded ones
   u32 const* slice_start;  // [n_slices][kClassStride] first slot of classes 1, 2; null with one class
@@ -136,6 +137,10 @@ struct CacheView {
                          // their code -- from the back, s = start_c+1 - 1 - j ("two-ended"), so one
                          // traversal fills both without knowing their numbers in advance.
   u32 rounds;            // exchange rounds = remote classes (0 with one rank)
+  u64 const* code_off;   // [n_slices * n_classes + 1]: the codes of class c of slice s start at
+                         // code_off[s * n_classes + c]; coded element j of lane l at + 32 j + l.  (Almost every
+                         // element carries the default coefficient, so a code per SLOT -- one byte in five of
+                         // the cache -- would be memory that is never read.)
 };
 
 // Class of the entry at position `pos` of the replicated vector for the rows of rank d.rank:
@@ -152,10 +157,15 @@ struct FillParams {
   TermsView terms;
   u64 const* slice_off;
   u32* idx;
-  void* code;              // u8 or u16 per slot, see code_wide
+  void* code;              // u8 or u16 per slot (see code_wide) of the slots from code_slot0 on: a temporary
+                           // that covers the rows of this launch only; the codes of the coded elements are
+                           // compacted afterwards (CacheView::code_off)
   dev_u16* len;            // [2 * n_classes][local rows] (see CacheView)
   u32 default_code;
   u32 pad1_;
+  u64 row_lo, row_hi;      // local rows of this launch (multiples of 32, or the end): the fill runs in row
+                           // chunks so that the code temporary stays small
+  u64 code_slot0;          // first slot `code` covers = slice_off[row_lo / 32]
   u32 const* slice_start;  // several classes, fill pass: [n_slices][kClassStride] (see CacheView); null otherwise
   int count_only;          // exact class sizes wanted: first pass, only `len` is written
   u32 n_classes;

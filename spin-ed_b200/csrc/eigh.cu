@@ -594,6 +594,102 @@ __global__ void __launch_bounds__(kThreads) row_transform_kernel(T* V, u64 ld, i
   }
 }
 
+// value as it will be read back from storage (single-precision storage rounds)
+template <class T> __device__ __forceinline__ typename VT<T>::Acc stored(typename VT<T>::Acc v) { return v; }
+template <> __device__ __forceinline__ double stored<float>(double v) { return (double)(float)v; }
+template <> __device__ __forceinline__ double2 stored<float2>(double2 v) { return make_double2((double)(float)v.x, (double)(float)v.y); }
+
+// Restart and residual in ONE pass over the basis (basis full, one wanted pair -- every iteration of
+// the 40-spin decks, whose basis holds three vectors): rows of V and W (n x m) <- rows * C (m x p),
+// in place, and column p of V <- r = sum_j (W_j - theta V_j) C[j][0], the residual of the first Ritz
+// pair (its coefficients are column 0 of C), unscaled: the next search direction.  Also
+// partial[b] = sum |r|^2 and partial[(1 + q) * grid + b] = sum conj(V'_q) r for q < p, so that the
+// orthogonalisation of r needs no pass of its own for the dot products.  Same arithmetic, in the same
+// order, as residual_block_kernel followed by row_transform_kernel on V and on W -- 6 column reads and
+// 5 writes for a 3-vector basis instead of 12 and 5.
+template <class T, int MAXM>
+__global__ void __launch_bounds__(kThreads) restart_residual_kernel(T* V, T* W, u64 ld, int m, int p, double2 const* C, double theta,
+                                                                    u64 n, double2* partial) {
+  using A = typename VT<T>::Acc;
+  __shared__ double2 c[MAXM * MAXM];
+  for (int j = threadIdx.x; j < m * p; j += blockDim.x) c[j] = C[j];
+  __syncthreads();
+  double2 nrm = make_double2(0, 0);
+  double2 dots[MAXM - 1];
+#pragma unroll
+  for (int q = 0; q < MAXM - 1; ++q) dots[q] = make_double2(0, 0);
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    A v[MAXM], w[MAXM];
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j)
+      if (j < m) {
+        v[j] = VT<T>::load(V + (u64)j * ld + i);
+        w[j] = VT<T>::load(W + (u64)j * ld + i);
+      }
+    A r = from2<A>(make_double2(0, 0));
+#pragma unroll
+    for (int j = 0; j < MAXM; ++j)
+      if (j < m) r = addv(r, mulc(subv(w[j], mulc(v[j], make_double2(theta, 0))), c[j * p]));
+    r = stored<T>(r);
+#pragma unroll
+    for (int q = 0; q < MAXM - 1; ++q)
+      if (q < p) {
+        A vq = from2<A>(make_double2(0, 0)), wq = from2<A>(make_double2(0, 0));
+#pragma unroll
+        for (int j = 0; j < MAXM; ++j)
+          if (j < m) {
+            vq = addv(vq, mulc(v[j], c[j * p + q]));
+            wq = addv(wq, mulc(w[j], c[j * p + q]));
+          }
+        VT<T>::store(V + (u64)q * ld + i, vq);
+        VT<T>::store(W + (u64)q * ld + i, wq);
+        dot_acc(dots[q], stored<T>(vq), r);
+      }
+    VT<T>::store(V + (u64)p * ld + i, r);
+    dot_acc(nrm, r, r);
+  }
+  block_reduce_store(nrm, partial + blockIdx.x);
+#pragma unroll
+  for (int q = 0; q < MAXM - 1; ++q)
+    if (q < p) block_reduce_store(dots[q], partial + (u64)(1 + q) * gridDim.x + blockIdx.x);
+}
+
+// w -= sum_j coeff[j] V_j (j < m) and partial[block] = sum |w|^2 of the result, in one pass
+template <class T>
+__global__ void __launch_bounds__(kThreads) axpy_norm_kernel(T const* V, u64 ld, int m, double2 const* coeff, T* w, u64 n,
+                                                             double2* partial) {
+  using A = typename VT<T>::Acc;
+  __shared__ double2 c[kMaxBasis];
+  for (int j = threadIdx.x; j < m; j += blockDim.x) c[j] = coeff[j];
+  __syncthreads();
+  double2 nrm = make_double2(0, 0);
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    A acc = VT<T>::load(w + i);
+    for (int j = 0; j < m; ++j) acc = subv(acc, mulc(VT<T>::load(V + (u64)j * ld + i), c[j]));
+    acc = stored<T>(acc);
+    VT<T>::store(w + i, acc);
+    dot_acc(nrm, acc, acc);
+  }
+  block_reduce_store(nrm, partial + blockIdx.x);
+}
+
+// w *= 1 / sqrt(norm2), or 0 when norm2 <= tiny * ref2 (linearly dependent on the basis).
+// record[0] = norm2 / ref2 = the share of the direction that survived the orthogonalisation; *flag is
+// raised when that is less than half (DGKS criterion for a second sweep).
+template <class T>
+__global__ void __launch_bounds__(kThreads) scale_rel_kernel(T* w, u64 n, double2 const* norm2, double2 const* ref2, double tiny,
+                                                             double* record, int* flag) {
+  double const v = norm2[0].x, ref = ref2[0].x;
+  double const kept = ref > 0 ? v / ref : 0.0;
+  double const s = kept > tiny ? rsqrt(v) : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *record = kept;
+    if (kept < 0.5) *flag = 1;
+  }
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    VT<T>::store(w + i, mulc(VT<T>::load(w + i), make_double2(s, 0)));
+}
+
 __device__ __forceinline__ u64 splitmix64(u64 z) {
   z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -840,7 +936,14 @@ struct Solver {
     int const kcap = (int)std::min<u64>(k, (u64)kMaxBasis);
     V.take(op, 0, ld * mmax);
     Wm.take(op, 1, ld * mmax);
-    resid.take(op, 2, ld * std::max(1, kcap));
+    // One wanted pair and a basis of at most 8 vectors (the 40/42-spin decks: 3 and 4): when the basis
+    // is full, restart and residual are one fused pass (restart_residual_kernel), the residual lands
+    // unscaled in the first free column with its dot products against the restarted basis, and one
+    // fused axpy + norm pass orthogonalises it; while the basis grows, the residual is written
+    // straight into the next column.  No separate residual buffer exists in this mode (one vector
+    // of 6.9 GB for chain_40 on one GPU).
+    bool const single = k == 1 && mmax <= 8 && mmax >= 2 && (u64)mmax < n_global;
+    resid.take(op, 2, single ? 1 : ld * std::max(1, kcap));
     if (cm.active()) xfull.take(op, 3, chunk * cm.world);
     partial.take(op, 4, (size_t)grid * kMaxBasis * kGroup);
     scal.take(op, 5, kMaxBasis);
@@ -904,6 +1007,65 @@ struct Solver {
     double a_norm = 0;
     int status = SPED_NOT_CONVERGED;
     int const max_outer = 200000;
+    // Restart coefficients for nb new directions: C = [S(:, 0:r) | previous Ritz directions
+    // orthogonalised against it] (the "+k" of GD+k), as columns over the current basis of m vectors.
+    auto restart_columns = [&](int nb) {
+      int r = std::min(std::max(keep, (int)std::min<u64>(k, (u64)m)), mmax - nb);
+      r = std::max(r, 1);
+      int p_room = mmax - nb - r;
+      std::vector<std::vector<cplx>> cols;
+      for (int q = 0; q < r; ++q) {
+        std::vector<cplx> c(m);
+        for (int j = 0; j < m; ++j) c[j] = S[(size_t)j * m + q];
+        cols.push_back(c);
+      }
+      for (int q = 0; q < n_prev && p_room > 0; ++q) {
+        std::vector<cplx> c(m, cplx(0, 0));
+        for (int j = 0; j < m_prev; ++j) c[j] = S_prev[(size_t)j * n_prev + q];
+        for (int pass = 0; pass < 2; ++pass)
+          for (auto const& u : cols) {
+            cplx d = 0;
+            for (int j = 0; j < m; ++j) d += std::conj(u[j]) * c[j];
+            for (int j = 0; j < m; ++j) c[j] -= d * u[j];
+          }
+        double nn = 0;
+        for (auto const& v : c) nn += std::norm(v);
+        if (nn < 1e-20) continue;
+        for (auto& v : c) v /= std::sqrt(nn);
+        cols.push_back(c);
+        --p_room;
+      }
+      return cols;
+    };
+    // bookkeeping of a restart with the columns `cols`: H <- C^H H C, Ritz vectors become unit vectors
+    auto restart_projection = [&](std::vector<std::vector<cplx>> const& cols) {
+      int const p = (int)cols.size();
+      std::vector<cplx> Hn((size_t)p * p, cplx(0, 0));
+      for (int a = 0; a < p; ++a)
+        for (int c2 = 0; c2 < p; ++c2) {
+          cplx acc = 0;
+          for (int i = 0; i < m; ++i) {
+            cplx t = 0;
+            for (int j = 0; j < m; ++j) t += Hat(i, j) * cols[c2][j];
+            acc += std::conj(cols[a][i]) * t;
+          }
+          Hn[(size_t)a * p + c2] = acc;
+        }
+      for (int a = 0; a < p; ++a)
+        for (int c2 = 0; c2 < p; ++c2) Hat(a, c2) = Hn[(size_t)a * p + c2];
+      // after the transform the first r Ritz vectors are the unit vectors e_0..e_{r-1}
+      S.assign((size_t)p * p, cplx(0, 0));
+      for (int q = 0; q < p; ++q) S[(size_t)q * p + q] = 1.0;
+      m = p;
+      ++stats.restarts;
+    };
+    auto flatten = [&](std::vector<std::vector<cplx>> const& cols, int rows) {
+      int const p = (int)cols.size();
+      std::vector<cplx> C((size_t)rows * p);
+      for (int q = 0; q < p; ++q)
+        for (int j = 0; j < rows; ++j) C[(size_t)j * p + q] = cols[q][j];
+      return C;
+    };
     for (int it = 0; it < max_outer; ++it) {
       stats.iterations = it + 1;
       std::vector<cplx> Hm((size_t)m * m);
@@ -914,7 +1076,29 @@ struct Solver {
       int const kk = (int)std::min<u64>(k, (u64)m);
       // residuals of ALL wanted pairs, kGroup per pass over V and W, one round trip for their norms
       bool const have_all = m >= (int)k;
-      {
+      bool fused = false;  // this iteration restarted inside the residual pass: r sits in V[:, m], unscaled
+      if (single && m == mmax) {
+        SPED_NVTX("sped_eigh: restart + residual (fused)");
+        auto cols = restart_columns(1);
+        int const p = (int)cols.size();
+        std::vector<cplx> C = flatten(cols, m);
+        std::vector<double2> c(C.size());
+        for (size_t i = 0; i < c.size(); ++i) c[i] = make_double2(C[i].real(), C[i].imag());
+        CUDA_CHECK(cudaMemcpyAsync(transform_coeff.ptr, c.data(), c.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+        if (m <= 4) restart_residual_kernel<T, 4><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, p, transform_coeff.ptr, theta[0], n, partial.ptr);
+        else restart_residual_kernel<T, 8><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, p, transform_coeff.ptr, theta[0], n, partial.ptr);
+        KERNEL_LAUNCHED();
+        // scal[0] = |r|^2, scal[1 + q] = <V'_q, r>: left on the device for the orthogonalisation below
+        finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, 1 + p, scal.ptr);
+        KERNEL_LAUNCHED();
+        comm_allreduce_sum_f64(reinterpret_cast<double*>(scal.ptr), 2 * (size_t)(1 + p), stream);
+        auto r2 = to_host(scal.ptr, 1);
+        rn[0] = std::sqrt(std::max(0.0, r2[0].real()));
+        ev[0] = theta[0];
+        restart_projection(cols);
+        fused = true;
+        timer.mark(PhaseTimer::kRestart);
+      } else {
         SPED_NVTX("sped_eigh: residuals");
         std::vector<double2> sblock;
         std::vector<double> th;
@@ -929,7 +1113,7 @@ struct Solver {
           }
           CUDA_CHECK(cudaMemcpyAsync(coeff.ptr, sblock.data(), sizeof(double2) * sblock.size(), cudaMemcpyHostToDevice, stream));
           CUDA_CHECK(cudaMemcpyAsync(d_theta.ptr, th.data(), sizeof(double) * kq, cudaMemcpyHostToDevice, stream));
-          T* out = resid.ptr + (u64)q0 * ld;
+          T* out = single ? V.ptr + (u64)m * ld : resid.ptr + (u64)q0 * ld;  // single: m < mmax here, column m is free
           switch (kq) {
             case 1: residual_block_kernel<T, 1><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
             case 2: residual_block_kernel<T, 2><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
@@ -974,56 +1158,11 @@ struct Solver {
       // restart when the new directions do not fit
       if (m + nb > mmax) {
         SPED_NVTX("sped_eigh: restart");
-        int r = std::min(std::max(keep, (int)std::min<u64>(k, (u64)m)), mmax - nb);
-        r = std::max(r, 1);
-        int p_room = mmax - nb - r;
-        // coefficient block C = [S(:, 0:r) | previous Ritz directions orthogonalised against it]
-        std::vector<std::vector<cplx>> cols;
-        for (int q = 0; q < r; ++q) {
-          std::vector<cplx> c(m);
-          for (int j = 0; j < m; ++j) c[j] = S[(size_t)j * m + q];
-          cols.push_back(c);
-        }
-        for (int q = 0; q < n_prev && p_room > 0; ++q) {
-          std::vector<cplx> c(m, cplx(0, 0));
-          for (int j = 0; j < m_prev; ++j) c[j] = S_prev[(size_t)j * n_prev + q];
-          for (int pass = 0; pass < 2; ++pass)
-            for (auto const& u : cols) {
-              cplx d = 0;
-              for (int j = 0; j < m; ++j) d += std::conj(u[j]) * c[j];
-              for (int j = 0; j < m; ++j) c[j] -= d * u[j];
-            }
-          double nn = 0;
-          for (auto const& v : c) nn += std::norm(v);
-          if (nn < 1e-20) continue;
-          for (auto& v : c) v /= std::sqrt(nn);
-          cols.push_back(c);
-          --p_room;
-        }
-        int p = (int)cols.size();
-        std::vector<cplx> C((size_t)m * p);
-        for (int q = 0; q < p; ++q)
-          for (int j = 0; j < m; ++j) C[(size_t)j * p + q] = cols[q][j];
-        transform(V.ptr, m, p, C);
-        transform(Wm.ptr, m, p, C);
-        std::vector<cplx> Hn((size_t)p * p, cplx(0, 0));
-        for (int a = 0; a < p; ++a)
-          for (int c2 = 0; c2 < p; ++c2) {
-            cplx acc = 0;
-            for (int i = 0; i < m; ++i) {
-              cplx t = 0;
-              for (int j = 0; j < m; ++j) t += Hat(i, j) * cols[c2][j];
-              acc += std::conj(cols[a][i]) * t;
-            }
-            Hn[(size_t)a * p + c2] = acc;
-          }
-        for (int a = 0; a < p; ++a)
-          for (int c2 = 0; c2 < p; ++c2) Hat(a, c2) = Hn[(size_t)a * p + c2];
-        // after the transform the first r Ritz vectors are the unit vectors e_0..e_{r-1}
-        S.assign((size_t)p * p, cplx(0, 0));
-        for (int q = 0; q < p; ++q) S[(size_t)q * p + q] = 1.0;
-        m = p;
-        ++stats.restarts;
+        auto cols = restart_columns(nb);
+        std::vector<cplx> C = flatten(cols, m);
+        transform(V.ptr, m, (int)cols.size(), C);
+        transform(Wm.ptr, m, (int)cols.size(), C);
+        restart_projection(cols);
         timer.mark(PhaseTimer::kRestart);
       }
       // remember the current Ritz directions (for the "+k" part of the next restart)
@@ -1037,16 +1176,35 @@ struct Solver {
       // (the basis is still smaller than the number of wanted pairs) is a random vector
       int const m_old = m;
       std::vector<int> random_cols;
-      for (int q = 0; q < nb; ++q) {
+      bool const fused_ok = fused && nb == 1 && !unconverged.empty() && rn[0] > 0;
+      for (int q = 0; q < nb && !fused_ok; ++q) {
         T* dst = V.ptr + (u64)(m_old + q) * ld;
         if (q < (int)unconverged.size() && rn[unconverged[q]] > 0) {
-          copy_scaled_kernel<T><<<grid, kThreads, 0, stream>>>(resid.ptr + (u64)unconverged[q] * ld, ld, dst, ld, n, 1.0 / rn[unconverged[q]]);
+          // (single: the residual already sits in its column and is scaled in place)
+          T const* src = (single || fused) ? dst : resid.ptr + (u64)unconverged[q] * ld;
+          copy_scaled_kernel<T><<<grid, kThreads, 0, stream>>>(src, ld, dst, ld, n, 1.0 / rn[unconverged[q]]);
           KERNEL_LAUNCHED();
         } else {
           random_cols.push_back(q);
         }
       }
-      if (!random_cols.empty()) {
+      if (fused_ok) {
+        // r (unscaled, in column m_old) minus its components along the restarted basis -- the dot
+        // products came out of the fused pass -- and its norm in one pass; then the scaling.  The
+        // residual of a Ritz pair is orthogonal to the basis up to rounding, so this first sweep
+        // keeps nearly all of it; should it keep less than half, the gated second sweep runs.
+        SPED_NVTX("sped_eigh: orthogonalisation (fused)");
+        T* w = V.ptr + (u64)m_old * ld;
+        CUDA_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(int), stream));
+        axpy_norm_kernel<T><<<grid, kThreads, 0, stream>>>(V.ptr, ld, m_old, scal.ptr + 1, w, n, partial.ptr);
+        KERNEL_LAUNCHED();
+        finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, 1, scal.ptr + 32);
+        KERNEL_LAUNCHED();
+        comm_allreduce_sum_f64(reinterpret_cast<double*>(scal.ptr + 32), 2, stream);
+        scale_rel_kernel<T><<<grid, kThreads, 0, stream>>>(w, n, scal.ptr + 32, scal.ptr, 1e-24, d_norms.ptr, d_flag.ptr);
+        KERNEL_LAUNCHED();
+        ortho_sweep(m_old, w, 1, nullptr, nullptr, d_flag.ptr);
+      } else if (!random_cols.empty()) {
         // rare: place the residual-based directions first, then the random ones sequentially
         std::vector<int> res_cols;
         for (int q = 0; q < nb; ++q)

@@ -194,6 +194,8 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   fp.n_sid = n_sid;
   fp.code_wide = wide ? 1 : 0;
   fp.overflow = &overflow;
+  fp.row_lo = 0;
+  fp.row_hi = n_local;
   if (rounds > 0) {  // several ranks: exact class sizes from a counting traversal
     fp.count_only = 1;
     pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
@@ -227,13 +229,48 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   for (u64 s = 0; s < n_slices; ++s) slice_off[s + 1] = slice_off[s] + 32ull * widths[s];
   u64 const slots = slice_off[n_slices];
   std::vector<u32> idx(std::max<u64>(slots, 1), 0xdeadbeefu);
-  std::vector<unsigned char> code(std::max<u64>(slots, 1) * (wide ? 2 : 1), 0xee);
   fp.slice_off = slice_off.data();
   fp.idx = idx.data();
-  fp.code = code.data();
   std::fill(len.begin(), len.end(), 0);
-  pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
+  // The fill runs in row chunks (here: 3 slices each, so that even small decks take several); its
+  // one-code-per-slot temporary covers one chunk, and the codes of the coded elements are compacted
+  // chunk by chunk (code_width_kernel, slice_scan_kernel, code_compact_kernel), then concatenated.
+  u64 const slices_per_chunk = 3;
+  std::vector<u32> cw(std::max<u64>(n_slices * n_classes, 1), 0);
+  std::vector<unsigned char> compact;
+  CacheView v{};
+  v.slice_off = slice_off.data();
+  v.len = len.data();
+  v.slice_start = n_classes > 1 ? slice_start.data() : nullptr;
+  v.n_slices = n_slices;
+  v.n_classes = n_classes;
+  for (u64 s_lo = 0; s_lo < n_slices; s_lo += slices_per_chunk) {
+    u64 const s_hi = std::min(n_slices, s_lo + slices_per_chunk);
+    std::vector<unsigned char> temp(std::max<u64>(slice_off[s_hi] - slice_off[s_lo], 1) * (wide ? 2 : 1), 0xee);
+    fp.row_lo = 32 * s_lo;
+    fp.row_hi = std::min<u64>(32 * s_hi, n_local);
+    fp.code_slot0 = slice_off[s_lo];
+    fp.code = temp.data();
+    pr.with_canon([&](auto const& canon) { cache_fill_rows(fp, pr.terms, canon); });
+    code_width_kernel(len.data(), n_local, n_classes, s_lo, s_hi, cw.data());
+    u64 const regions = (s_hi - s_lo) * n_classes;
+    std::vector<u64> chunk_off(regions + 1, 0);
+    for (u64 k = 0; k < regions; ++k) chunk_off[k + 1] = chunk_off[k] + 32ull * cw[s_lo * n_classes + k];
+    std::vector<unsigned char> part(std::max<u64>(chunk_off[regions], 1) * (wide ? 2 : 1), 0xdd);
+    v.code = temp.data();
+    if (wide)
+      code_compact_kernel<std::uint16_t>(v, n_local, fp.row_lo, fp.row_hi, fp.code_slot0, chunk_off.data(),
+                                         reinterpret_cast<std::uint16_t*>(part.data()));
+    else
+      code_compact_kernel<std::uint8_t>(v, n_local, fp.row_lo, fp.row_hi, fp.code_slot0, chunk_off.data(), part.data());
+    compact.insert(compact.end(), part.begin(), part.begin() + chunk_off[regions] * (wide ? 2 : 1));
+  }
   if (overflow) fail(SPED_INTERNAL_ERROR, "emulated cache fill: a row exceeded its slot bound");
+  std::vector<u64> code_off(n_slices * n_classes + 1, 0);
+  for (u64 k = 0; k < n_slices * n_classes; ++k) code_off[k + 1] = code_off[k] + 32ull * cw[k];
+  u64 const code_slots = code_off[n_slices * n_classes];
+  if (compact.size() != code_slots * (wide ? 2 : 1)) fail(SPED_INTERNAL_ERROR, "emulation: the compact code stream does not add up");
+  compact.resize(std::max<u64>(code_slots, 1) * (wide ? 2 : 1), 0xdd);
   u64 elements = 0, dflt = 0;
   for (u32 seg = 0; seg < 2 * n_classes; ++seg)
     for (u64 i = 0; i < n_local; ++i) {
@@ -244,11 +281,13 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   stats[1] = elements;
   stats[2] = dflt;
   stats[3] = n_classes;
+  stats[4] = code_slots;
 
   // ---- streaming kernel: all classes in one pass, then class by class ----
   CachedParams cp{};
-  cp.cache = CacheView{slice_off.data(), idx.data(), code.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,
-                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, rounds};
+  cp.cache = CacheView{slice_off.data(), idx.data(), compact.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,
+                       table.data(), n_slices, wide ? 1 : 0, (u32)cm.n_codes, n_classes, near, cm.default_code, rounds,
+                       code_off.data()};
   cp.ctx = pr.ctx;
   cp.diag_re = pr.diag_re.data();
   cp.diag_im = cplx_diag ? pr.diag_im.data() : nullptr;

@@ -239,7 +239,8 @@ struct Operator {
   bool cache_rejected = false;  // decided not to (or failed to) build for this basis generation
   DeviceBuffer<u64> c_slice_off;
   DeviceBuffer<u32> c_idx;
-  DeviceBuffer<unsigned char> c_code;  // u8 or u16 per slot
+  DeviceBuffer<unsigned char> c_code;  // u8 or u16 per CODED element (compact, see CacheView::code_off)
+  DeviceBuffer<u64> c_code_off;        // [slices * classes + 1]
   int c_code_wide = 0;
   DeviceBuffer<std::uint16_t> c_len;   // [2 * c_classes][local rows]: default-coefficient / coded elements per source class
   DeviceBuffer<u32> c_slice_start;     // [slices][kClassStride] first slot of classes 1, 2 (several classes only)

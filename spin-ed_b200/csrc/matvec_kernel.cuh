@@ -227,7 +227,8 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
   u64 const n_local = dist.n_local;
   bool const count_only = p.count_only != 0;
   u32 const nc = p.n_classes;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
+  u64 const row_hi = p.row_hi < n_local ? p.row_hi : n_local;
+  for (u64 i = p.row_lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < row_hi; i += (u64)gridDim.x * blockDim.x) {
     u64 const row = dist_local_to_global(dist, i);
     u64 const r = ix.direct ? row : __ldg(ix.reps + row);
     u64 const slice = i >> 5;
@@ -265,8 +266,8 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u64 const at = base + (u64)(dflt ? lo + nd : hi - 1u - nx) * 32;
       p.idx[at] = (u32)pos;
       if (!dflt) {
-        if (p.code_wide) static_cast<dev_u16*>(p.code)[at] = (dev_u16)code;
-        else static_cast<dev_u8*>(p.code)[at] = (dev_u8)code;
+        if (p.code_wide) static_cast<dev_u16*>(p.code)[at - p.code_slot0] = (dev_u16)code;
+        else static_cast<dev_u8*>(p.code)[at - p.code_slot0] = (dev_u8)code;
       }
     });
     for (u32 c = 0; c < nc; ++c) {

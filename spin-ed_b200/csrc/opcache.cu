@@ -361,6 +361,7 @@ void Operator::drop_cache() {
   c_slice_off.release();
   c_idx.release();
   c_code.release();
+  c_code_off.release();
   c_len.release();
   c_slice_start.release();
   c_classes = 1;
@@ -446,8 +447,10 @@ bool Operator::cache_usable() {
   fp.code_wide = c_code_wide;
   fp.overflow = d_flag.ptr;
   // the matrix-free traversal (run-time specialised kernel when available)
+  fp.row_lo = 0;
+  fp.row_hi = n_local;
   auto launch_fill = [&]() {
-    int grid = persistent_grid(n_local, kThreads, 8);
+    int grid = persistent_grid(fp.row_hi - fp.row_lo, kThreads, 8);
     void* jit = sym ? jit_cache_fill_kernel(b) : nullptr;
     if (jit) {
       void* args[] = {&fp};
@@ -492,25 +495,106 @@ bool Operator::cache_usable() {
   KERNEL_LAUNCHED();
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
-  u64 need = c_slots * (4 + code_bytes) + n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 16 : 8) + n_codes * 24;
+  // What stays resident (the codes of the few coded elements come on top, counted below).  The fill
+  // writes one code per slot into a temporary and only the coded parts are kept (CacheView::code_off);
+  // it runs in row chunks so that the temporary stays below 2 GB instead of a fifth of the cache
+  // (chain_40 on one GPU: 20 GB that would not fit beside an 80 GB cache and the solver's vectors).
+  u64 const meta = n_local * 4 * c_classes + (c_slices + 1) * (c_classes > 1 ? 16 : 8) + (c_slices * c_classes + 1) * 8 + n_codes * 24;
+  u64 need = c_slots * 4 + meta;
+  u64 chunk_bytes = (u64)1 << 31;
+  if (char const* e = std::getenv("SPED_FILL_CHUNK_BYTES"))  // tests: force several chunks on small decks
+    if (*e) chunk_bytes = std::max<u64>(1, std::strtoull(e, nullptr, 10));
+  u64 const n_chunks = std::max<u64>(1, std::min<u64>(c_slices, (c_slots * code_bytes + chunk_bytes - 1) / chunk_bytes));
+  u64 const slices_per_chunk = (c_slices + n_chunks - 1) / n_chunks;
+  std::vector<u64> chunk_slot0(n_chunks + 1, 0);  // first slot of every chunk
+  u64 temp_slots = 0;
+  for (u64 k = 0; k <= n_chunks; ++k) {
+    u64 const sl = std::min(c_slices, k * slices_per_chunk);
+    CUDA_CHECK(cudaMemcpy(&chunk_slot0[k], c_slice_off.ptr + sl, 8, cudaMemcpyDeviceToHost));
+    if (k) temp_slots = std::max(temp_slots, chunk_slot0[k] - chunk_slot0[k - 1]);
+  }
+  u64 const peak = need + temp_slots * code_bytes + slices_per_chunk * c_classes * 8;
   size_t free_b = 0, total_b = 0;
   CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
   // automatic mode keeps room for what a solver typically allocates afterwards (a few more vectors of
   // the local rows); mode 1 only insists on the cache itself fitting
-  u64 const reserve = std::max<u64>((u64)2 << 30, 4 * n_local * 16);
+  // (what sped_eigh already holds on this operator -- it takes its workspace before the first
+  // application -- counts towards that room)
+  u64 held = 0;
+  for (auto const& w : eigh_ws) held += w.count;
+  u64 const wanted = 4 * n_local * 16;
+  u64 const reserve = std::max<u64>((u64)2 << 30, wanted > held ? wanted - held : 0);
   if (mode != 1 && need + reserve > free_b) return reject("does not fit in the free device memory (with room for the solver's vectors)");
-  if (need > free_b - free_b / 16) return reject("does not fit in device memory");
+  if (peak > free_b - free_b / 16) return reject("does not fit in device memory");
   c_idx.alloc(std::max<u64>(c_slots, 1));
-  c_code.alloc(std::max<u64>(c_slots, 1) * code_bytes);
+  DeviceBuffer<unsigned char> code_temp(std::max<u64>(temp_slots, 1) * code_bytes);
+  u64 const n_regions = c_slices * c_classes;
+  DeviceBuffer<u32> d_cw(std::max<u64>(n_regions, 1));
+  DeviceBuffer<u64> d_chunk_off(slices_per_chunk * c_classes + 1);
+  std::vector<DeviceBuffer<unsigned char>> chunk_codes(n_chunks);
+  std::vector<u64> chunk_code_slots(n_chunks, 0);
 
   fp.slice_off = c_slice_off.ptr;
   fp.idx = c_idx.ptr;
-  fp.code = c_code.ptr;
-  launch_fill();
+  fp.code = code_temp.ptr;
+  CacheView v{};  // what the compaction kernel reads
+  v.slice_off = c_slice_off.ptr;
+  v.code = code_temp.ptr;
+  v.len = c_len.ptr;
+  v.slice_start = c_slice_start.ptr;
+  v.n_slices = c_slices;
+  v.n_classes = c_classes;
+  for (u64 k = 0; k < n_chunks; ++k) {
+    u64 const s_lo = std::min(c_slices, k * slices_per_chunk), s_hi = std::min(c_slices, s_lo + slices_per_chunk);
+    if (s_lo == s_hi) continue;
+    fp.row_lo = 32 * s_lo;
+    fp.row_hi = std::min<u64>(32 * s_hi, n_local);
+    fp.code_slot0 = chunk_slot0[k];
+    launch_fill();
+    // widths of this chunk's coded regions, their offsets inside the chunk, the compact codes
+    u64 const regions = (s_hi - s_lo) * c_classes;
+    code_width_kernel<<<persistent_grid(s_hi - s_lo, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, s_lo, s_hi, d_cw.ptr);
+    KERNEL_LAUNCHED();
+    slice_scan_kernel<<<1, 1024>>>(d_cw.ptr + s_lo * c_classes, d_chunk_off.ptr, regions);
+    KERNEL_LAUNCHED();
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpy(&chunk_code_slots[k], d_chunk_off.ptr + regions, 8, cudaMemcpyDeviceToHost));
+    if (chunk_code_slots[k]) {
+      chunk_codes[k].alloc(chunk_code_slots[k] * code_bytes);
+      int const grid = persistent_grid(fp.row_hi - fp.row_lo, kThreads, 8);
+      if (c_code_wide)
+        code_compact_kernel<std::uint16_t><<<grid, kThreads>>>(v, n_local, fp.row_lo, fp.row_hi, fp.code_slot0, d_chunk_off.ptr,
+                                                              reinterpret_cast<std::uint16_t*>(chunk_codes[k].ptr));
+      else
+        code_compact_kernel<std::uint8_t><<<grid, kThreads>>>(v, n_local, fp.row_lo, fp.row_hi, fp.code_slot0, d_chunk_off.ptr,
+                                                             reinterpret_cast<std::uint8_t*>(chunk_codes[k].ptr));
+      KERNEL_LAUNCHED();
+      CUDA_CHECK(cudaGetLastError());
+    }
+  }
   CUDA_CHECK(cudaDeviceSynchronize());
   int overflow = 0;
   CUDA_CHECK(cudaMemcpy(&overflow, d_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
   if (overflow) return reject("internal: a row exceeded its slot bound");
+  {  // global offsets of the coded regions; the chunks' codes, concatenated, are the compact stream
+    code_temp.release();
+    c_code_off.alloc(n_regions + 1);
+    slice_scan_kernel<<<1, 1024>>>(d_cw.ptr, c_code_off.ptr, n_regions);
+    KERNEL_LAUNCHED();
+    CUDA_CHECK(cudaGetLastError());
+    u64 code_slots = 0;
+    CUDA_CHECK(cudaMemcpy(&code_slots, c_code_off.ptr + n_regions, 8, cudaMemcpyDeviceToHost));
+    c_code.alloc(std::max<u64>(code_slots, 1) * code_bytes);
+    u64 at = 0;
+    for (u64 k = 0; k < n_chunks; ++k) {
+      if (chunk_code_slots[k])
+        CUDA_CHECK(cudaMemcpy(c_code.ptr + at * code_bytes, chunk_codes[k].ptr, chunk_code_slots[k] * code_bytes, cudaMemcpyDeviceToDevice));
+      at += chunk_code_slots[k];
+      chunk_codes[k].release();
+    }
+    if (at != code_slots) return reject("internal: the compact code stream does not add up");
+    need += code_slots * code_bytes;
+  }
   cache_bytes = need;
   cache_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   cache_ready = true;
@@ -546,7 +630,7 @@ void Operator::cached_matmat(int dtype, u64 block, void const* x, u64 xs, void* 
   MatvecParams mp = operator_params(*this);
   CachedParams p{};
   p.cache = CacheView{c_slice_off.ptr, c_idx.ptr, c_code.ptr, c_len.ptr, c_slice_start.ptr, c_table.ptr, c_slices,
-                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_rounds};
+                      c_code_wide, (u32)(c_table.count / 3), c_classes, c_near, c_default_code, c_rounds, c_code_off.ptr};
   p.phase = phase;
   p.beside_transfer = beside_transfer ? 1 : 0;
   p.mean_row_length = dist.n_local ? (float)((double)c_slots / (double)dist.n_local) : 0.0f;

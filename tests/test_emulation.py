@@ -24,7 +24,7 @@ def _emulate(op, reps, stab, world, rank, x, ncols=1):
     dt = x.dtype
     outs = [np.full(max(n_local, 1), 7.0, dtype=dt) for _ in range(3)]
     block = np.full((max(n_local, 1), max(ncols, 1)), 7.0, dtype=dt, order="F")
-    stats = (C.c_uint64 * 4)()
+    stats = (C.c_uint64 * 5)()
     ffi.checkStatus(ffi.emulLib().sped_selftest_emulate_matvec(
         op._ptr, n, reps.ctypes.data, stab.ctypes.data, world, rank, ffi.DTYPE_TAGS[np.dtype(dt)], x.ctypes.data,
         outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, stats, ncols, block.ctypes.data))
@@ -65,6 +65,10 @@ def test_emulated_kernels_match_oracle(oracle, name, groups, monkeypatch):
             rounds = 0 if world == 1 else 1 if (world == 2 or ONE_ROUND) else 2
             assert stats[3] == 1 + rounds
             assert stats[0] >= stats[1] >= stats[2]
+            # compact code stream: room for every coded element, never more than one entry per slot,
+            # and nothing at all when every element carries the default coefficient
+            assert stats[1] - stats[2] <= stats[4] <= stats[0]
+            assert (stats[4] == 0) == (stats[1] == stats[2])
             for what, got in (("matrix-free", free), ("cached, one pass", allc), ("cached, class by class", phased)):
                 err = np.linalg.norm(got - want[rows])
                 assert err <= 1e-12 * scale, (name, world, rank, what, err / scale)

@@ -217,6 +217,41 @@ def test_eigh_small_basis_restarts_like_the_40_spin_decks(oracle):
     assert st["restarts"] > 0 and st["matvecs"] >= st["iterations"]
 
 
+@pytest.mark.parametrize("mmax", [2, 3, 4, 5, 8])
+def test_eigh_single_pair_small_basis_fused_restart(oracle, mmax):
+    """One wanted pair and a basis of <= 8 vectors: restart + residual are one fused pass and the
+    residual goes straight into the next basis column (eigh.cu, `single`).  Same eigenvalue as the
+    dense spectrum, residual within tolerance, eigenvector an eigenvector -- real and complex."""
+    for cfg, dt in ((decks.chain(16, 8, 1, (0, 0)), np.float64), (extra_configs()["chain_8_k1_complex"], np.complex128),
+                    (decks.chain(14, 7, None, (0, 0)), np.complex128)):
+        ob, terms = oracle_problem(oracle, cfg)
+        ob.build()
+        dense = oracle.Operator(ob, terms).to_dense()
+        want = np.linalg.eigvalsh(dense)[0]
+        uc = product_problem(cfg)
+        ffi.buildBasis(uc.cBasis)
+        op = uc.cHamiltonian.operatorObject
+        ev, vecs, rn = ffi.eigh(op, dt, 1, maxBasisSize=mmax)
+        st = ffi.eighLastStats(op)
+        scale = np.abs(np.linalg.eigvalsh(dense)).max()
+        assert abs(ev[0] - want) <= 1e-10 * scale, (mmax, dt, ev[0], want)
+        assert rn[0] <= 1e-8 * scale
+        v = vecs[:, 0] if vecs.ndim == 2 else vecs
+        assert abs(np.linalg.norm(v) - 1) < 1e-10
+        assert np.linalg.norm(dense @ v - ev[0] * v) <= 1e-8 * scale
+        if ob.number_states > 3 * mmax:
+            assert st["restarts"] > 0
+
+
+def test_eigh_single_pair_float32_storage_small_basis():
+    cfg = decks.load("heisenberg_square_4x4")
+    uc = product_problem(cfg)
+    ffi.buildBasis(uc.cBasis)
+    ev, vecs, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float32, 1, maxBasisSize=3)
+    assert vecs.dtype == np.float32
+    assert abs(ev[0] + 44.9139328337) < 2e-3
+
+
 def test_eigh_float32_storage(oracle):
     cfg = decks.load("heisenberg_square_4x4")  # the deck asks for float32 (SpinED.hs:344-352)
     uc = product_problem(cfg)
@@ -306,6 +341,30 @@ def test_operator_cache_agrees_with_matrix_free(oracle, name):
             assert np.linalg.norm(free - cached) <= tol * np.linalg.norm(free), (name, dt, block)
             again = ffi.apply(op, x)
             assert again.tobytes() == cached.tobytes()
+
+
+@pytest.mark.parametrize("name", ["heisenberg_chain_10", "chain_12_pi", "chain_8_k1_complex", "heisenberg_triangular_19",
+                                  "heisenberg_square_5x5"])
+def test_operator_cache_fill_in_row_chunks(name, monkeypatch):
+    """The cache fill runs in row chunks (its one-code-per-slot temporary covers one chunk) and keeps
+    only the codes of the coded elements.  Chunks of a few hundred bytes force many of them on small
+    decks: the cache must be the same size and give the same bits as the one filled in one piece."""
+    cfg = _cfg(name) if name in ALL_SMALL else decks.load(name)
+    results = []
+    for chunk in ("", "300", "1"):
+        monkeypatch.setenv("SPED_FILL_CHUNK_BYTES", chunk)
+        uc = product_problem(cfg)
+        ffi.buildBasis(uc.cBasis)
+        op = uc.cHamiltonian.operatorObject
+        n = ffi.getNumberStates(uc.cBasis)
+        dt = np.float64 if ffi.isOperatorReal(op) else np.complex128
+        x = np.asfortranarray(np.stack([splitmix_vector(n, 77 + c, dt) for c in range(3)], axis=1))
+        ffi.operatorSetCache(op, 1)
+        y = ffi.apply(op, x)
+        info = ffi.operatorCacheInfo(op)
+        assert info["ready"]
+        results.append((y.tobytes(), info["bytes"]))
+    assert results[0] == results[1] == results[2]
 
 
 def test_jit_and_interpreted_kernels_agree_bitwise(monkeypatch):
