@@ -193,6 +193,7 @@ struct Basis {
 };
 
 std::shared_ptr<Basis> make_basis(std::shared_ptr<Group> g, unsigned n_spins, int hw, int inv);
+void jit_prefetch(Basis& b);  // jit.cpp: start compiling the specialised cache-fill kernel in the background
 
 // ---- interactions / operator (operator.cu) ----
 struct Interaction {

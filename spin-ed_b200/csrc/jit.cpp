@@ -10,11 +10,16 @@
 #include <nvrtc.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
+#include <future>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
 #include <sstream>
 #include <tuple>
 
@@ -274,11 +279,21 @@ struct Gen {
   }
 };
 
+// A compilation in flight: NVRTC runs on its own thread (it needs neither the device nor the basis
+// object -- only the generated source), started when the basis is built, so that it overlaps the
+// enumeration of the representatives instead of preceding the first application of an operator.
+struct Pending {
+  std::shared_future<std::vector<char>> cubin;
+  std::chrono::steady_clock::time_point started;
+  double expected_seconds = 0;  // rough: 0.25 s + 4 ms per program step on the hosts measured
+};
+
 // one loaded module = one kernel: the matrix-free matvec of a (dtype, columns) pair, or the cache fill
 struct Entry {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;
   bool failed = false;
+  std::shared_ptr<Pending> pending;
 };
 constexpr int kKindMatvec = 0, kKindFill = 1;
 
@@ -381,11 +396,17 @@ void write_cached_cubin(std::string const& path, std::vector<char> const& cubin)
   if (!ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
 }
 
-std::vector<char> compile_cubin(Basis& b, int kind, int dtype, int nb) {
-  std::vector<char> cubin;
+// generated header of one module: kind, storage type, columns, and the canonicalisation as code
+std::string module_header(Basis const& b, int kind, int dtype, int nb) {
   std::string program = Gen(b.program).run();
-  std::string header = std::string("#define SPED_JIT_KIND ") + std::to_string(kind) + "\n#define SPED_T " + dtype_name(dtype) +
-                       "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
+  return std::string("#define SPED_JIT_KIND ") + std::to_string(kind) + "\n#define SPED_T " + dtype_name(dtype) +
+         "\n#define SPED_NB " + std::to_string(nb) + "\n" + program;
+}
+
+// header -> cubin (disk cache, else NVRTC).  Touches no basis and no CUDA context: safe on any thread
+// once nvrtc() has been called on the thread that starts it.
+std::vector<char> compile_header(std::string const& header) {
+  std::vector<char> cubin;
   std::string cache_file = cubin_cache_path(header);
   if (!cache_file.empty()) {
     cubin = read_cached_cubin(cache_file);
@@ -433,14 +454,58 @@ std::vector<char> compile_cubin(Basis& b, int kind, int dtype, int nb) {
   return cubin;
 }
 
-Entry compile(Basis& b, int kind, int dtype, int nb) {
-  Entry out;
-  auto t0 = std::chrono::steady_clock::now();
-  std::vector<char> cubin = compile_cubin(b, kind, dtype, nb);
+std::vector<char> compile_cubin(Basis& b, int kind, int dtype, int nb) { return compile_header(module_header(b, kind, dtype, nb)); }
+
+// Compilations still running when the process ends are waited for before the statics they use go
+// away (a basis handle may be leaked, or destroyed by a finaliser at exit).
+struct InFlight {
+  std::mutex m;
+  std::vector<std::shared_future<std::vector<char>>> futures;
+  void add(std::shared_future<std::vector<char>> f) {
+    std::lock_guard<std::mutex> lock(m);
+    futures.erase(std::remove_if(futures.begin(), futures.end(),
+                                 [](auto const& x) { return x.wait_for(std::chrono::seconds(0)) == std::future_status::ready; }),
+                  futures.end());
+    futures.push_back(std::move(f));
+  }
+  ~InFlight() {
+    for (auto& f : futures) f.wait();
+  }
+};
+InFlight& in_flight() {
+  nvrtc();  // constructed first, hence destroyed after this object
+  static InFlight x;
+  return x;
+}
+
+// SPED_JIT_WAIT=1: always wait for the specialised kernel (tests that must exercise it; benchmarks of
+// the kernel itself).  Default: never stall a launch on NVRTC when the interpreted kernel gets the work
+// done sooner.
+bool jit_always_wait() {
+  char const* e = std::getenv("SPED_JIT_WAIT");
+  return e && e[0] == '1';
+}
+
+void start_compile(Basis& b, Entry& e, int kind, int dtype, int nb) {
+  auto p = std::make_shared<Pending>();
+  std::string header = module_header(b, kind, dtype, nb);
+  p->started = std::chrono::steady_clock::now();
+  p->expected_seconds = 0.25 + 0.004 * (double)b.program.steps.size();
+  InFlight& reg = in_flight();
+  p->cubin = std::async(std::launch::async, [header = std::move(header)]() { return compile_header(header); }).share();
+  reg.add(p->cubin);
+  e.pending = std::move(p);
+}
+
+// cubin -> loaded module; called on the thread that launches (the device context must be current)
+void finish_compile(Basis& b, Entry& out, int kind, int dtype, int nb) {
+  std::vector<char> cubin = out.pending->cubin.get();
+  double const dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - out.pending->started).count();
+  out.pending.reset();
   size_t size = cubin.size();
   if (cubin.empty()) {
     out.failed = true;
-    return out;
+    return;
   }
   cudaError_t e = cudaLibraryLoadData(&out.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&out.kernel, out.lib, kind == kKindFill ? "sped_cache_fill_jit" : "sped_matvec_jit");
@@ -450,23 +515,44 @@ Entry compile(Basis& b, int kind, int dtype, int nb) {
     cudaGetLastError();
     out.failed = true;
     out.kernel = nullptr;
-    return out;
+    return;
   }
-  double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  SPED_LOG("jit: specialised %s (%s, %d columns, %zu steps) ready in %.2f s, cubin %zu bytes",
+  SPED_LOG("jit: specialised %s (%s, %d columns, %zu steps) ready %.2f s after it was requested, cubin %zu bytes",
            kind == kKindFill ? "cache fill" : "matvec", dtype_name(dtype), nb, b.program.steps.size(), dt, size);
-  return out;
 }
 
-void* jit_kernel(Basis& b, int kind, int dtype, int nb) {
+// The specialised kernel, or null: not available (no NVRTC, SPED_JIT=0, trivial group, failure) -- or
+// still compiling while the interpreted kernel is expected to finish the work at hand sooner.
+// `images` = canonicalisation steps the launches at hand perform (rows x transitions per row x group
+// order x traversals); the interpreted kernel needs about 0.55 ps more per image than the specialised
+// one (6x6 on B200: 358 against 167 ms for 3.4e11 images).  images < 0: request only, never wait.
+void* jit_kernel(Basis& b, int kind, int dtype, int nb, double images) {
   if (!jit_enabled() || b.trivial()) return nullptr;
   std::lock_guard<std::mutex> lock(g_jit_mutex);
   if (!b.jit_cache) b.jit_cache = std::make_shared<Cache>();
   Cache& c = *static_cast<Cache*>(b.jit_cache.get());
   auto key = std::make_tuple(kind, dtype, nb);
   auto it = c.entries.find(key);
-  if (it == c.entries.end()) it = c.entries.emplace(key, compile(b, kind, dtype, nb)).first;
-  return it->second.failed ? nullptr : (void*)it->second.kernel;
+  if (it == c.entries.end()) {
+    it = c.entries.emplace(key, Entry{}).first;
+    start_compile(b, it->second, kind, dtype, nb);
+  }
+  Entry& e = it->second;
+  if (e.pending) {
+    bool const ready = e.pending->cubin.wait_for(std::chrono::seconds(0)) == std::future_status::ready;
+    if (!ready && !jit_always_wait()) {
+      if (images < 0) return nullptr;
+      double const elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - e.pending->started).count();
+      double const remaining = std::max(0.05, e.pending->expected_seconds - elapsed);
+      double const extra_if_interpreted = images * 0.55e-12;
+      if (extra_if_interpreted < remaining) {
+        SPED_LOG("jit: %s kernel still compiling (%.2f s so far); the interpreted kernel runs this time", kind == kKindFill ? "cache-fill" : "matvec", elapsed);
+        return nullptr;
+      }
+    }
+    finish_compile(b, e, kind, dtype, nb);
+  }
+  return e.failed ? nullptr : (void*)e.kernel;
 }
 
 }  // namespace
@@ -482,9 +568,19 @@ size_t jit_compile_only(Basis& b, int dtype, int nb) {
 // Source of the specialised canonicalisation (exposed for tests and inspection).
 std::string jit_program_source(Basis const& b) { return Gen(b.program).run(); }
 
-void* jit_matvec_kernel(Basis& b, int dtype, int nb) { return jit_kernel(b, kKindMatvec, dtype, nb); }
+void* jit_matvec_kernel(Basis& b, int dtype, int nb, double images) { return jit_kernel(b, kKindMatvec, dtype, nb, images); }
 
 // The cache fill does not depend on the storage type: one module per basis.
-void* jit_cache_fill_kernel(Basis& b) { return jit_kernel(b, kKindFill, SPED_F64, 1); }
+void* jit_cache_fill_kernel(Basis& b, double images) { return jit_kernel(b, kKindFill, SPED_F64, 1, images); }
+
+// Called when a basis is built: the operator cache of any operator on it will want the fill kernel.
+void jit_prefetch(Basis& b) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {  // nothing could launch it
+    cudaGetLastError();
+    return;
+  }
+  jit_kernel(b, kKindFill, SPED_F64, 1, -1.0);
+}
 
 }  // namespace sped

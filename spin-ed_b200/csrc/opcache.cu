@@ -24,7 +24,7 @@ namespace sped {
 
 ProgramView<u32> program_view32(Basis const& b, size_t& smem, bool& staged);
 ProgramView<u64> program_view64(Basis const& b, size_t& smem, bool& staged);
-void* jit_cache_fill_kernel(Basis& b);
+void* jit_cache_fill_kernel(Basis& b, double images);
 MatvecParams operator_params(Operator& op);
 
 namespace {
@@ -449,9 +449,12 @@ bool Operator::cache_usable() {
   // the matrix-free traversal (run-time specialised kernel when available)
   fp.row_lo = 0;
   fp.row_hi = n_local;
+  // one choice for the whole build (one or two traversals of the local rows): the specialised kernel if
+  // it is ready or worth waiting for, else the interpreted one -- the two give identical results
+  double const images = (double)n_local * (double)b.group_order() * 0.5 * (double)mp.terms.n_bonds * (two ? 2.0 : 1.0);
+  void* const jit = sym ? jit_cache_fill_kernel(b, images) : nullptr;
   auto launch_fill = [&]() {
     int grid = persistent_grid(fp.row_hi - fp.row_lo, kThreads, 8);
-    void* jit = sym ? jit_cache_fill_kernel(b) : nullptr;
     if (jit) {
       void* args[] = {&fp};
       if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(jit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));

@@ -17,7 +17,7 @@ namespace sped {
 
 ProgramView<u32> program_view32(Basis const& b, size_t& smem, bool& staged);
 ProgramView<u64> program_view64(Basis const& b, size_t& smem, bool& staged);
-void* jit_matvec_kernel(Basis& b, int dtype, int nb);  // jit.cpp; nullptr = not available
+void* jit_matvec_kernel(Basis& b, int dtype, int nb, double images);  // jit.cpp; nullptr = not available (or not worth waiting for)
 
 namespace {
 
@@ -245,7 +245,9 @@ void launch_matvec(Operator& op, MatvecParams p, int dtype, u64 block, u64 xs, u
     p.y = y + c0 * ys;
     bool wide = left > 1;
     p.ncols = (u32)std::min<u64>(left, wide ? 4 : 1);
-    void* jit = sym ? jit_matvec_kernel(b, dtype, wide ? 4 : 1) : nullptr;
+    // canonicalisation steps of this launch (about half of the bonds of a row have a transition)
+    double const images = (double)n_local * (double)b.group_order() * 0.5 * (double)p.terms.n_bonds;
+    void* jit = sym ? jit_matvec_kernel(b, dtype, wide ? 4 : 1, images) : nullptr;
     if (jit) {
       // run-time specialised kernel: same device code, canonicalisation emitted as straight-line code
       void* args[] = {&p};
