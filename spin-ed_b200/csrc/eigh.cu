@@ -307,16 +307,23 @@ __global__ void __launch_bounds__(kThreads) multi_dot_kernel(T const* V, u64 ld,
   }
 }
 
-// out[j] = sum_b partial[j * nblocks + b]  in fixed order (one thread per j)
-__global__ void finish_dot_kernel(double2 const* partial, int nblocks, int ncols, double2* out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
+// out[j] = sum_b partial[j * nblocks + b] in a fixed order: one warp per j, lane l takes the blocks
+// l, l + 32, ... and the lanes are combined by a shuffle tree.  (One thread per j walked its 592
+// partials one dependent load after the other: 57 us per call, several calls per iteration -- 0.17 s of
+// the 0.40 s xxz_triangular_19 solve.)
+__global__ void __launch_bounds__(32) finish_dot_kernel(double2 const* partial, int nblocks, int ncols, double2* out) {
+  int const j = blockIdx.x;
   if (j >= ncols) return;
   double2 s = make_double2(0, 0);
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = threadIdx.x; b < nblocks; b += 32) {
     s.x += partial[(u64)j * nblocks + b].x;
     s.y += partial[(u64)j * nblocks + b].y;
   }
-  out[j] = s;
+  for (int o = 16; o; o >>= 1) {
+    s.x += __shfl_down_sync(0xffffffffu, s.x, o);
+    s.y += __shfl_down_sync(0xffffffffu, s.y, o);
+  }
+  if (threadIdx.x == 0) out[j] = s;
 }
 
 // w -= sum_j coeff[j] V_j
@@ -795,7 +802,7 @@ struct Solver {
       default: block_dot_kernel<T, 4><<<grid, kThreads, 0, stream>>>(Vp, ld, m, W, ld, n, partial.ptr, gate); break;
     }
     KERNEL_LAUNCHED();
-    finish_dot_kernel<<<(m * nw + 63) / 64, 64, 0, stream>>>(partial.ptr, grid, m * nw, out);
+    finish_dot_kernel<<<m * nw, 32, 0, stream>>>(partial.ptr, grid, m * nw, out);
     KERNEL_LAUNCHED();
     comm_allreduce_sum_f64(reinterpret_cast<double*>(out), 2 * (size_t)m * nw, stream);
   }
@@ -1089,7 +1096,7 @@ struct Solver {
         else restart_residual_kernel<T, 8><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, p, transform_coeff.ptr, theta[0], n, partial.ptr);
         KERNEL_LAUNCHED();
         // scal[0] = |r|^2, scal[1 + q] = <V'_q, r>: left on the device for the orthogonalisation below
-        finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, 1 + p, scal.ptr);
+        finish_dot_kernel<<<1 + p, 32, 0, stream>>>(partial.ptr, grid, 1 + p, scal.ptr);
         KERNEL_LAUNCHED();
         comm_allreduce_sum_f64(reinterpret_cast<double*>(scal.ptr), 2 * (size_t)(1 + p), stream);
         auto r2 = to_host(scal.ptr, 1);
@@ -1121,7 +1128,7 @@ struct Solver {
             default: residual_block_kernel<T, 4><<<grid, kThreads, 0, stream>>>(V.ptr, Wm.ptr, ld, m, coeff.ptr, d_theta.ptr, out, ld, n, partial.ptr); break;
           }
           KERNEL_LAUNCHED();
-          finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, kq, scal.ptr + off);
+          finish_dot_kernel<<<kq, 32, 0, stream>>>(partial.ptr, grid, kq, scal.ptr + off);
           KERNEL_LAUNCHED();
           off += kq;
         }
@@ -1198,7 +1205,7 @@ struct Solver {
         CUDA_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(int), stream));
         axpy_norm_kernel<T><<<grid, kThreads, 0, stream>>>(V.ptr, ld, m_old, scal.ptr + 1, w, n, partial.ptr);
         KERNEL_LAUNCHED();
-        finish_dot_kernel<<<1, 64, 0, stream>>>(partial.ptr, grid, 1, scal.ptr + 32);
+        finish_dot_kernel<<<1, 32, 0, stream>>>(partial.ptr, grid, 1, scal.ptr + 32);
         KERNEL_LAUNCHED();
         comm_allreduce_sum_f64(reinterpret_cast<double*>(scal.ptr + 32), 2, stream);
         scale_rel_kernel<T><<<grid, kThreads, 0, stream>>>(w, n, scal.ptr + 32, scal.ptr, 1e-24, d_norms.ptr, d_flag.ptr);

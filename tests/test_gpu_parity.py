@@ -381,7 +381,7 @@ def test_cache_filled_by_either_kernel_is_the_same(monkeypatch):
         ffi.buildBasis(uc.cBasis)
         op = uc.cHamiltonian.operatorObject
         ffi.operatorSetCache(op, 1)
-        x = splitmix_vector(ffi.getNumberStates(uc.cBasis), 9, np.float64)
+        x = splitmix_vector(ffi.getNumberStates(uc.cBasis), 9, np.complex128)  # complex characters (k != 0)
         outs.append(ffi.apply(op, x).tobytes())
         assert ffi.operatorCacheInfo(op)["ready"]
     assert outs[0] == outs[1] == outs[2]
