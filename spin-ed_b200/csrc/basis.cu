@@ -352,8 +352,8 @@ static u64 binom_host(int n, int k) {
 void Basis::build() {
   std::lock_guard<std::mutex> lock(mutex);
   SPED_NVTX("sped: ls_build (enumerate representatives)");
-  ensure_device_tables();
   jit_prefetch(*this);  // NVRTC of the cache-fill kernel runs on its own thread beside the enumeration
+  ensure_device_tables();
   auto t0 = std::chrono::steady_clock::now();
   Comm& cm = comm();
   u64 const expected = expected_dimension();
@@ -494,8 +494,8 @@ void Basis::build() {
 void Basis::adopt(u64 size, u64 const* reps_in) {
   std::lock_guard<std::mutex> lock(mutex);
   SPED_NVTX("sped: ls_build_unsafe (adopt representatives)");
-  ensure_device_tables();
   jit_prefetch(*this);
+  ensure_device_tables();
   auto t0 = std::chrono::steady_clock::now();
   built = false;  // a failing ls_build_unsafe must not leave the previous basis marked as built
   index = BasisIndex{};

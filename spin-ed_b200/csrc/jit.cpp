@@ -300,8 +300,12 @@ constexpr int kKindMatvec = 0, kKindFill = 1;
 struct Cache {
   std::map<std::tuple<int, int, int>, Entry> entries;  // (kind, dtype, columns)
   ~Cache() {
-    for (auto& e : entries)
+    for (auto& e : entries) {
+      // a compilation still in flight is waited for: once the last handle is gone the process may
+      // exit, and NVRTC must not be running while its own statics are torn down
+      if (e.second.pending) e.second.pending->cubin.wait();
       if (e.second.lib) cudaLibraryUnload(e.second.lib);
+    }
   }
 };
 
@@ -472,8 +476,21 @@ struct InFlight {
     for (auto& f : futures) f.wait();
   }
 };
+// One trivial synchronous compilation before the registry below is constructed: NVRTC creates its
+// lazily initialised statics (and registers their destructors) now, so that at exit the registry --
+// registered later, hence run earlier -- has waited for every compile thread before they go away.
+void warm_up_nvrtc() {
+  NvrtcApi& api = nvrtc();
+  if (!api.handle) return;
+  nvrtcProgram prog = nullptr;
+  if (api.CreateProgram(&prog, "extern \"C\" __global__ void sped_warm_up() {}\n", "sped_warm_up.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return;
+  char const* opts[] = {"--gpu-architecture=sm_100a"};
+  api.CompileProgram(prog, 1, opts);
+  api.DestroyProgram(&prog);
+}
 InFlight& in_flight() {
-  nvrtc();  // constructed first, hence destroyed after this object
+  static bool const warmed = (warm_up_nvrtc(), true);  // also loads NVRTC: constructed first, destroyed last
+  (void)warmed;
   static InFlight x;
   return x;
 }
@@ -575,8 +592,10 @@ void* jit_cache_fill_kernel(Basis& b, double images) { return jit_kernel(b, kKin
 
 // Called when a basis is built: the operator cache of any operator on it will want the fill kernel.
 void jit_prefetch(Basis& b) {
+  char const* force = std::getenv("SPED_JIT_PREFETCH");  // 0: never; 1: even without a device (host-side tests)
+  if (force && force[0] == '0') return;
   int n_dev = 0;
-  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {  // nothing could launch it
+  if (!(force && force[0] == '1') && (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)) {  // nothing could launch it
     cudaGetLastError();
     return;
   }
