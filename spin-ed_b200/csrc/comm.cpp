@@ -10,8 +10,13 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "internal.h"
+
+#if !defined(SPED_CE_DEFAULT)
+#define SPED_CE_DEFAULT 0  // opt-in (SPED_EXCHANGE=ce) until measured on 4 and 8 GPUs
+#endif
 
 namespace sped {
 
@@ -66,6 +71,33 @@ void nccl_check(ncclResult_t r, char const* what) {
 
 Comm g_comm;
 
+constexpr int kCeStreams = 4;
+
+struct CeExchange {
+  size_t bytes = 0;                  // capacity of each send buffer
+  void* send[2] = {nullptr, nullptr};
+  std::vector<void*> peer[2];        // peer[q][p]: send buffer q of rank p mapped into this process (own: send[q])
+  cudaStream_t streams[kCeStreams] = {};
+  cudaEvent_t ev_start = nullptr, ev_done[kCeStreams] = {};
+  unsigned long long* d_word = nullptr;  // the barrier's all-reduce operand
+  unsigned char* d_handles = nullptr;    // staging of the IPC handles for their all-gather
+  unsigned long long counter = 0;
+  bool streams_ready = false;
+};
+CeExchange g_ce;
+
+void ce_release_buffers() {
+  for (int q = 0; q < 2; ++q) {
+    for (size_t p = 0; p < g_ce.peer[q].size(); ++p)
+      if ((int)p != g_comm.rank && g_ce.peer[q][p]) cudaIpcCloseMemHandle(g_ce.peer[q][p]);
+    g_ce.peer[q].clear();
+    if (g_ce.send[q]) cudaFree(g_ce.send[q]);
+    g_ce.send[q] = nullptr;
+  }
+  g_ce.bytes = 0;
+}
+
+
 }  // namespace
 
 Comm& comm() { return g_comm; }
@@ -99,6 +131,16 @@ void comm_init(int world, int rank, void const* id128) {
 }
 
 void comm_finalize() {
+  if (g_ce.streams_ready) {
+    cudaDeviceSynchronize();
+    ce_release_buffers();
+    for (auto& st : g_ce.streams) cudaStreamDestroy(st);
+    cudaEventDestroy(g_ce.ev_start);
+    for (auto& ev : g_ce.ev_done) cudaEventDestroy(ev);
+    cudaFree(g_ce.d_word);
+    cudaFree(g_ce.d_handles);
+    g_ce = CeExchange{};
+  }
   if (g_comm.nccl) {
     api().CommDestroy(static_cast<ncclComm_t>(g_comm.nccl));
     g_comm.nccl = nullptr;
@@ -140,6 +182,96 @@ void comm_exchange_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cuda
   }
   nccl_check(api().GroupEnd(), "ncclGroupEnd");
 }
+
+// ---- exchange by the copy engines over peer memory -------------------------------------------
+// Long shards only (the 40/42-spin chains: hundreds of MB per shard): the one-word all-reduce and
+// the per-peer copy launches cost tens of microseconds, which a 16-32 MB shard exchange (6x6 over 4-8
+// ranks, 0.2 ms with one NCCL all-gather) cannot spare.  SPED_EXCHANGE=ce / nccl forces either.
+bool comm_ce_wanted(size_t chunk_bytes) {
+  if (!g_comm.active()) return false;
+  char const* e = std::getenv("SPED_EXCHANGE");
+  if (e && e[0] == 'c') return true;
+  if (e && e[0] == 'n') return false;
+  return SPED_CE_DEFAULT && chunk_bytes >= ((size_t)64 << 20);
+}
+
+void comm_ce_prepare(size_t chunk_bytes) {
+  if (chunk_bytes <= g_ce.bytes) return;
+  ncclComm_t c = static_cast<ncclComm_t>(g_comm.nccl);
+  int const P = g_comm.world;
+  if (!g_ce.streams_ready) {
+    for (auto& st : g_ce.streams) CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ce.ev_start, cudaEventDisableTiming));
+    for (auto& ev : g_ce.ev_done) CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_CHECK(cudaMalloc((void**)&g_ce.d_word, 8));
+    CUDA_CHECK(cudaMemset(g_ce.d_word, 0, 8));
+    CUDA_CHECK(cudaMalloc((void**)&g_ce.d_handles, (size_t)P * 2 * sizeof(cudaIpcMemHandle_t)));
+    g_ce.streams_ready = true;
+  }
+  // nobody may still be reading the old buffers: everything queued so far completes on every rank
+  CUDA_CHECK(cudaDeviceSynchronize());
+  nccl_check(api().AllReduce(g_ce.d_word, g_ce.d_word, 1, ncclUint64, ncclSum, c, g_comm.stream), "ncclAllReduce (barrier)");
+  CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
+  ce_release_buffers();
+  size_t const cap = chunk_bytes + chunk_bytes / 8;  // some slack: a wider storage type next time need not remap
+  cudaIpcMemHandle_t mine[2];
+  for (int q = 0; q < 2; ++q) {
+    CUDA_CHECK(cudaMalloc(&g_ce.send[q], cap));
+    CUDA_CHECK(cudaMemset(g_ce.send[q], 0, cap));
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine[q], g_ce.send[q]));
+  }
+  size_t const hb = 2 * sizeof(cudaIpcMemHandle_t);
+  CUDA_CHECK(cudaMemcpy(g_ce.d_handles + (size_t)g_comm.rank * hb, mine, hb, cudaMemcpyHostToDevice));
+  nccl_check(api().AllGather(g_ce.d_handles + (size_t)g_comm.rank * hb, g_ce.d_handles, hb, ncclChar, c, g_comm.stream),
+             "ncclAllGather (IPC handles)");
+  CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
+  std::vector<cudaIpcMemHandle_t> all((size_t)P * 2);
+  CUDA_CHECK(cudaMemcpy(all.data(), g_ce.d_handles, (size_t)P * hb, cudaMemcpyDeviceToHost));
+  for (int q = 0; q < 2; ++q) {
+    g_ce.peer[q].assign(P, nullptr);
+    for (int p = 0; p < P; ++p) {
+      if (p == g_comm.rank) {
+        g_ce.peer[q][p] = g_ce.send[q];
+        continue;
+      }
+      CUDA_CHECK(cudaIpcOpenMemHandle(&g_ce.peer[q][p], all[(size_t)p * 2 + q], cudaIpcMemLazyEnablePeerAccess));
+    }
+  }
+  g_ce.bytes = cap;
+  SPED_LOG("copy-engine exchange: two send buffers of %.1f MB mapped from %d peers", cap / 1e6, P - 1);
+}
+
+void comm_ce_publish(void const* shard, size_t bytes, cudaStream_t s) {
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(g_ce.send[g_ce.counter & 1], shard, bytes, cudaMemcpyDeviceToDevice, s));
+}
+
+void comm_ce_barrier(cudaStream_t g) {
+  nccl_check(api().AllReduce(g_ce.d_word, g_ce.d_word, 1, ncclUint64, ncclSum, static_cast<ncclComm_t>(g_comm.nccl), g),
+             "ncclAllReduce (exchange barrier)");
+}
+
+void comm_ce_pull_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cudaStream_t g) {
+  if (d_lo > d_hi) return;
+  int const P = g_comm.world, r = g_comm.rank, q = (int)(g_ce.counter & 1);
+  char* base = static_cast<char*>(buf);
+  CUDA_CHECK(cudaEventRecord(g_ce.ev_start, g));
+  int used = 0;
+  for (int d = d_lo; d <= d_hi; ++d) {
+    int const from = (r + d) % P, k = (d - d_lo) % kCeStreams;
+    if (k >= used) {
+      CUDA_CHECK(cudaStreamWaitEvent(g_ce.streams[k], g_ce.ev_start, 0));
+      used = k + 1;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(base + (size_t)from * chunk_bytes, g_ce.peer[q][from], chunk_bytes, cudaMemcpyDeviceToDevice,
+                               g_ce.streams[k]));
+  }
+  for (int k = 0; k < used; ++k) {
+    CUDA_CHECK(cudaEventRecord(g_ce.ev_done[k], g_ce.streams[k]));
+    CUDA_CHECK(cudaStreamWaitEvent(g, g_ce.ev_done[k], 0));
+  }
+}
+
+void comm_ce_advance() { ++g_ce.counter; }
 
 void comm_allreduce_sum_f64(double* dev, size_t count, cudaStream_t s) {
   if (!g_comm.active() || count == 0) return;

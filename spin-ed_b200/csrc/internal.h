@@ -150,6 +150,18 @@ void comm_allgather_inplace(void* buf, size_t chunk_bytes, cudaStream_t s);
 // one round of the shard exchange: this rank's chunk goes to ranks rank-d and the chunks of ranks
 // rank+d arrive in place, for d in [d_lo, d_hi] (mod world); grouped NCCL send/recv
 void comm_exchange_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cudaStream_t s);
+// ---- shard exchange by the copy engines over peer memory (comm.cpp) ----
+// Every rank publishes its shard in an IPC-shared send buffer (two of them, used in turn), a
+// one-word all-reduce tells everybody that all shards are in place, and each rank PULLS the shards of
+// its peers with cudaMemcpyAsync on a few copy streams: the copy engines move the data over NVLink,
+// no SM runs a transfer kernel beside the gather-bound passes of the product.
+bool comm_ce_wanted(size_t chunk_bytes);      // same answer on every rank: world, shard size, environment
+void comm_ce_prepare(size_t chunk_bytes);     // collective: (re)allocate and map the send buffers when they grow
+void comm_ce_publish(void const* shard, size_t bytes, cudaStream_t s);
+void comm_ce_barrier(cudaStream_t g);         // all shards of this exchange are published
+// shards of ranks rank+d, d in [d_lo, d_hi], into their places of buf; complete in stream order on g
+void comm_ce_pull_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cudaStream_t g);
+void comm_ce_advance();                       // next exchange uses the other send buffer
 void comm_allreduce_sum_f64(double* dev, size_t count, cudaStream_t s);
 void comm_allreduce_sum_u64(unsigned long long* dev, size_t count, cudaStream_t s);
 void comm_broadcast_bytes(void* dev, size_t bytes, int root, cudaStream_t s);

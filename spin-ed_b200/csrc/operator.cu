@@ -439,22 +439,33 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
     if (trace) CUDA_CHECK(cudaEventRecord(t[k], st));
   };
   cudaStream_t const g = cm.gather_stream;
-  // exchange: one all-gather, or two rounds of peer groups (near ranks first)
+  // exchange: one all-gather, or two rounds of peer groups (near ranks first) -- NCCL kernels, or the
+  // copy engines pulling the peers' published shards over peer memory (comm.cpp; long shards)
+  bool const ce = comm_ce_wanted(dist.chunk * es);
+  if (ce) {
+    comm_ce_prepare(dist.chunk * es);  // collective; does something only when the send buffers must grow
+    comm_ce_publish(x_local, n_local * es, s);
+  }
   CUDA_CHECK(cudaEventRecord(cm.ev_ready, s));
   CUDA_CHECK(cudaStreamWaitEvent(g, cm.ev_ready, 0));
   mark(0, g);
+  if (ce) comm_ce_barrier(g);
   if (rounds) {
     // (near comes from the world size, not from this rank's cache: a rank without rows or without a
     // cache has to send and receive in the same rounds as everybody else)
     int const near = (int)exchange_near(dist.world, dist.chunk);
-    comm_exchange_round(xfull, dist.chunk * es, 1, near, g);
+    if (ce) comm_ce_pull_round(xfull, dist.chunk * es, 1, near, g);
+    else comm_exchange_round(xfull, dist.chunk * es, 1, near, g);
     CUDA_CHECK(cudaEventRecord(cm.ev_round1, g));
     mark(1, g);
-    comm_exchange_round(xfull, dist.chunk * es, near + 1, (int)dist.world - 1, g);
+    if (ce) comm_ce_pull_round(xfull, dist.chunk * es, near + 1, (int)dist.world - 1, g);
+    else comm_exchange_round(xfull, dist.chunk * es, near + 1, (int)dist.world - 1, g);
   } else {
-    comm_allgather_inplace(xfull, dist.chunk * es, g);
+    if (ce) comm_ce_pull_round(xfull, dist.chunk * es, 1, (int)dist.world - 1, g);
+    else comm_allgather_inplace(xfull, dist.chunk * es, g);
     mark(1, g);
   }
+  if (ce) comm_ce_advance();
   CUDA_CHECK(cudaEventRecord(cm.ev_gathered, g));
   mark(2, g);
   if (!cached) {  // no rows, or matrix-free mode: wait for the whole vector, one kernel
