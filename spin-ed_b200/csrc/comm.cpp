@@ -128,6 +128,18 @@ void comm_init(int world, int rank, void const* id128) {
   CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_ready, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_gathered, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&g_comm.ev_round1, cudaEventDisableTiming));
+  // NCCL sets its channels up at the first collective of each kind (about a second on 8 GPUs): do that
+  // here, as part of bringing the communicator up, not inside the first solve
+  {
+    unsigned char* d_tmp = nullptr;
+    CUDA_CHECK(cudaMalloc((void**)&d_tmp, (size_t)world * 16));
+    CUDA_CHECK(cudaMemset(d_tmp, 0, (size_t)world * 16));
+    nccl_check(api().AllReduce(d_tmp, d_tmp, 2, ncclDouble, ncclSum, c, g_comm.stream), "ncclAllReduce (warm-up)");
+    CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
+    nccl_check(api().AllGather(d_tmp + (size_t)rank * 16, d_tmp, 16, ncclChar, c, g_comm.gather_stream), "ncclAllGather (warm-up)");
+    CUDA_CHECK(cudaStreamSynchronize(g_comm.gather_stream));
+    cudaFree(d_tmp);
+  }
 }
 
 void comm_finalize() {
