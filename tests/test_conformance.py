@@ -22,6 +22,19 @@ def test_header_compiles_as_c_and_links(tmp_path):
     _build(tmp_path, "conformance_full.c")  # takes the address of all 32 ls_* symbols: a missing export is a link error
 
 
+@pytest.mark.parametrize("destroy", [False, True])
+def test_process_may_exit_while_nvrtc_compiles(tmp_path, destroy):
+    """ls_build starts NVRTC on a background thread; a process that ends at once -- basis destroyed or
+    leaked -- must exit cleanly (seen once as SIGILL in the C conformance driver before the
+    compilation was waited for)."""
+    exe = _build(tmp_path, "exit_race.c")
+    env = dict(os.environ, SPED_JIT_PREFETCH="1", SPED_CACHE_DIR="")
+    for _ in range(3):
+        out = subprocess.run([exe] + (["destroy"] if destroy else []), capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+        assert "build rc" in out.stdout
+
+
 @pytest.mark.gpu
 def test_c_driver_runs_the_reference_call_sequence(tmp_path):
     out = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=300)
