@@ -698,8 +698,18 @@ def run_ours(args):
     # 1/2/4/8 B200); step-time roofline fraction included.  On ONE GPU its operator cache (80 GB) and
     # a 3-vector solver just fit: one (cold) solve only, to keep the default run within minutes.
     sharded = {}
+    s = None
     if args.sharded_deck and args.sharded_deck != args.config and (world > 1 or not args.no_sharded_at_one):
-        s = bench_deck(ctx, args.sharded_deck, args, headline=False, solves="both" if world > 1 else "cold")
+        try:
+            s = bench_deck(ctx, args.sharded_deck, args, headline=False, solves="both" if world > 1 else "cold")
+        except Exception as e:  # noqa: BLE001 -- one GPU only: the headline line must survive (several ranks would hang anyway)
+            if world > 1:
+                raise
+            log(f"[rank {rank}] {args.sharded_deck}: failed on one GPU: {e!r}")
+            s = None
+            extra[args.sharded_deck.replace("heisenberg_", "")] = {"workload": args.sharded_deck, "error": repr(e)}
+            ctx.torch.cuda.empty_cache()
+    if s is not None:
         sx = s["extra"]
         sharded = {
             "workload": s["name"], "rows": s["rows"], "offdiag_elements": s["n_off"], "ms_per_step": s["ms_per_step"],

@@ -83,20 +83,13 @@ struct CeExchange {
   unsigned char* d_handles = nullptr;    // staging of the IPC handles for their all-gather
   unsigned long long counter = 0;
   bool streams_ready = false;
+  bool unavailable = false;  // set on every rank alike when the IPC set-up failed somewhere
 };
 CeExchange g_ce;
 
-void ce_release_buffers() {
-  for (int q = 0; q < 2; ++q) {
-    for (size_t p = 0; p < g_ce.peer[q].size(); ++p)
-      if ((int)p != g_comm.rank && g_ce.peer[q][p]) cudaIpcCloseMemHandle(g_ce.peer[q][p]);
-    g_ce.peer[q].clear();
-    if (g_ce.send[q]) cudaFree(g_ce.send[q]);
-    g_ce.send[q] = nullptr;
-  }
-  g_ce.bytes = 0;
-}
-
+// Peers' mappings are closed before anybody frees the memory behind them: with `collective` a
+// barrier separates the two steps on all ranks (the callers guarantee every rank is here).
+void ce_release_buffers(bool collective);
 
 }  // namespace
 
@@ -145,7 +138,7 @@ void comm_init(int world, int rank, void const* id128) {
 void comm_finalize() {
   if (g_ce.streams_ready) {
     cudaDeviceSynchronize();
-    ce_release_buffers();
+    ce_release_buffers(false);  // teardown: other ranks may already be gone
     for (auto& st : g_ce.streams) cudaStreamDestroy(st);
     cudaEventDestroy(g_ce.ev_start);
     for (auto& ev : g_ce.ev_done) cudaEventDestroy(ev);
@@ -196,6 +189,28 @@ void comm_exchange_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cuda
 }
 
 // ---- exchange by the copy engines over peer memory -------------------------------------------
+namespace {
+void ce_release_buffers(bool collective) {
+  bool const any = g_ce.send[0] || g_ce.send[1];
+  for (int q = 0; q < 2; ++q) {
+    for (size_t p = 0; p < g_ce.peer[q].size(); ++p)
+      if ((int)p != g_comm.rank && g_ce.peer[q][p]) cudaIpcCloseMemHandle(g_ce.peer[q][p]);
+    g_ce.peer[q].clear();
+  }
+  if (collective && g_comm.nccl && g_ce.d_word) {
+    nccl_check(api().AllReduce(g_ce.d_word, g_ce.d_word, 1, ncclUint64, ncclSum, static_cast<ncclComm_t>(g_comm.nccl), g_comm.stream),
+               "ncclAllReduce (barrier)");
+    CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
+  }
+  (void)any;
+  for (int q = 0; q < 2; ++q) {
+    if (g_ce.send[q]) cudaFree(g_ce.send[q]);
+    g_ce.send[q] = nullptr;
+  }
+  g_ce.bytes = 0;
+}
+}  // namespace
+
 // Long shards only (the 40/42-spin chains: hundreds of MB per shard): the one-word all-reduce and
 // the per-peer copy launches cost tens of microseconds, which a 16-32 MB shard exchange (6x6 over 4-8
 // ranks, 0.2 ms with one NCCL all-gather) cannot spare.  SPED_EXCHANGE=ce / nccl forces either.
@@ -207,8 +222,11 @@ bool comm_ce_wanted(size_t chunk_bytes) {
   return SPED_CE_DEFAULT && chunk_bytes >= ((size_t)64 << 20);
 }
 
-void comm_ce_prepare(size_t chunk_bytes) {
-  if (chunk_bytes <= g_ce.bytes) return;
+// Collective.  False -- on every rank alike -- when some rank could not set its side up (no memory for
+// the send buffers, no IPC / peer access between the GPUs): the exchange then stays on NCCL for good.
+bool comm_ce_prepare(size_t chunk_bytes) {
+  if (g_ce.unavailable) return false;
+  if (chunk_bytes <= g_ce.bytes) return true;
   ncclComm_t c = static_cast<ncclComm_t>(g_comm.nccl);
   int const P = g_comm.world;
   if (!g_ce.streams_ready) {
@@ -224,33 +242,63 @@ void comm_ce_prepare(size_t chunk_bytes) {
   CUDA_CHECK(cudaDeviceSynchronize());
   nccl_check(api().AllReduce(g_ce.d_word, g_ce.d_word, 1, ncclUint64, ncclSum, c, g_comm.stream), "ncclAllReduce (barrier)");
   CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
-  ce_release_buffers();
+  ce_release_buffers(true);
   size_t const cap = chunk_bytes + chunk_bytes / 8;  // some slack: a wider storage type next time need not remap
+  // Every rank goes through the same collectives whatever fails locally; the failures are counted at the end.
+  unsigned long long failed = 0;
+  if (char const* e = std::getenv("SPED_EXCHANGE_TEST_FAIL"))  // test hook: pretend this rank cannot set its side up
+    if (*e && std::atoi(e) == g_comm.rank) failed = 1;
   cudaIpcMemHandle_t mine[2];
-  for (int q = 0; q < 2; ++q) {
-    CUDA_CHECK(cudaMalloc(&g_ce.send[q], cap));
-    CUDA_CHECK(cudaMemset(g_ce.send[q], 0, cap));
-    CUDA_CHECK(cudaIpcGetMemHandle(&mine[q], g_ce.send[q]));
+  std::memset(mine, 0, sizeof mine);
+  for (int q = 0; q < 2 && !failed; ++q) {
+    if (cudaMalloc(&g_ce.send[q], cap) != cudaSuccess || cudaMemset(g_ce.send[q], 0, cap) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine[q], g_ce.send[q]) != cudaSuccess) {
+      cudaGetLastError();
+      failed = 1;
+    }
   }
   size_t const hb = 2 * sizeof(cudaIpcMemHandle_t);
   CUDA_CHECK(cudaMemcpy(g_ce.d_handles + (size_t)g_comm.rank * hb, mine, hb, cudaMemcpyHostToDevice));
   nccl_check(api().AllGather(g_ce.d_handles + (size_t)g_comm.rank * hb, g_ce.d_handles, hb, ncclChar, c, g_comm.stream),
              "ncclAllGather (IPC handles)");
+  unsigned long long* d_failed = nullptr;
+  CUDA_CHECK(cudaMalloc((void**)&d_failed, 8));
+  CUDA_CHECK(cudaMemcpyAsync(d_failed, &failed, 8, cudaMemcpyHostToDevice, g_comm.stream));
+  nccl_check(api().AllReduce(d_failed, d_failed, 1, ncclUint64, ncclSum, c, g_comm.stream), "ncclAllReduce (IPC set-up)");
+  unsigned long long failed_anywhere = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&failed_anywhere, d_failed, 8, cudaMemcpyDeviceToHost, g_comm.stream));
   CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
   std::vector<cudaIpcMemHandle_t> all((size_t)P * 2);
   CUDA_CHECK(cudaMemcpy(all.data(), g_ce.d_handles, (size_t)P * hb, cudaMemcpyDeviceToHost));
-  for (int q = 0; q < 2; ++q) {
-    g_ce.peer[q].assign(P, nullptr);
-    for (int p = 0; p < P; ++p) {
-      if (p == g_comm.rank) {
-        g_ce.peer[q][p] = g_ce.send[q];
-        continue;
+  if (!failed_anywhere) {  // every rank has its buffers: map the peers', then agree once more
+    for (int q = 0; q < 2; ++q) {
+      g_ce.peer[q].assign(P, nullptr);
+      for (int p = 0; p < P; ++p) {
+        if (p == g_comm.rank) {
+          g_ce.peer[q][p] = g_ce.send[q];
+        } else if (cudaIpcOpenMemHandle(&g_ce.peer[q][p], all[(size_t)p * 2 + q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          g_ce.peer[q][p] = nullptr;
+          failed = 1;
+        }
       }
-      CUDA_CHECK(cudaIpcOpenMemHandle(&g_ce.peer[q][p], all[(size_t)p * 2 + q], cudaIpcMemLazyEnablePeerAccess));
     }
+    CUDA_CHECK(cudaMemcpyAsync(d_failed, &failed, 8, cudaMemcpyHostToDevice, g_comm.stream));
+    nccl_check(api().AllReduce(d_failed, d_failed, 1, ncclUint64, ncclSum, c, g_comm.stream), "ncclAllReduce (IPC mapping)");
+    CUDA_CHECK(cudaMemcpyAsync(&failed_anywhere, d_failed, 8, cudaMemcpyDeviceToHost, g_comm.stream));
+    CUDA_CHECK(cudaStreamSynchronize(g_comm.stream));
+  }
+  cudaFree(d_failed);
+  if (failed_anywhere) {
+    ce_release_buffers(true);
+    g_ce.unavailable = true;
+    SPED_LOG("copy-engine exchange not available (%llu rank(s) could not allocate or map the send buffers): the exchange stays on NCCL",
+             failed_anywhere);
+    return false;
   }
   g_ce.bytes = cap;
   SPED_LOG("copy-engine exchange: two send buffers of %.1f MB mapped from %d peers", cap / 1e6, P - 1);
+  return true;
 }
 
 void comm_ce_publish(void const* shard, size_t bytes, cudaStream_t s) {

@@ -156,7 +156,8 @@ void comm_exchange_round(void* buf, size_t chunk_bytes, int d_lo, int d_hi, cuda
 // its peers with cudaMemcpyAsync on a few copy streams: the copy engines move the data over NVLink,
 // no SM runs a transfer kernel beside the gather-bound passes of the product.
 bool comm_ce_wanted(size_t chunk_bytes);      // same answer on every rank: world, shard size, environment
-void comm_ce_prepare(size_t chunk_bytes);     // collective: (re)allocate and map the send buffers when they grow
+bool comm_ce_prepare(size_t chunk_bytes);     // collective: (re)allocate and map the send buffers when they grow;
+                                              // false on every rank alike when that is not possible (stay on NCCL)
 void comm_ce_publish(void const* shard, size_t bytes, cudaStream_t s);
 void comm_ce_barrier(cudaStream_t g);         // all shards of this exchange are published
 // shards of ranks rank+d, d in [d_lo, d_hi], into their places of buf; complete in stream order on g

@@ -564,6 +564,9 @@ bool Operator::cache_usable() {
     CUDA_CHECK(cudaMemcpy(&chunk_code_slots[k], d_chunk_off.ptr + regions, 8, cudaMemcpyDeviceToHost));
     if (chunk_code_slots[k]) {
       chunk_codes[k].alloc(chunk_code_slots[k] * code_bytes);
+      // (entries past a lane's own coded elements are padding nobody reads; zeroed so that the copy
+      // below moves initialised memory only)
+      CUDA_CHECK(cudaMemsetAsync(chunk_codes[k].ptr, 0, chunk_code_slots[k] * code_bytes));
       int const grid = persistent_grid(fp.row_hi - fp.row_lo, kThreads, 8);
       if (c_code_wide)
         code_compact_kernel<std::uint16_t><<<grid, kThreads>>>(v, n_local, fp.row_lo, fp.row_hi, fp.code_slot0, d_chunk_off.ptr,

@@ -441,11 +441,9 @@ void Operator::matvec_sharded(int dtype, void const* x_local, void* y_local, voi
   cudaStream_t const g = cm.gather_stream;
   // exchange: one all-gather, or two rounds of peer groups (near ranks first) -- NCCL kernels, or the
   // copy engines pulling the peers' published shards over peer memory (comm.cpp; long shards)
-  bool const ce = comm_ce_wanted(dist.chunk * es);
-  if (ce) {
-    comm_ce_prepare(dist.chunk * es);  // collective; does something only when the send buffers must grow
-    comm_ce_publish(x_local, n_local * es, s);
-  }
+  // (comm_ce_prepare is collective and does something only when the send buffers must grow)
+  bool const ce = comm_ce_wanted(dist.chunk * es) && comm_ce_prepare(dist.chunk * es);
+  if (ce) comm_ce_publish(x_local, n_local * es, s);
   CUDA_CHECK(cudaEventRecord(cm.ev_ready, s));
   CUDA_CHECK(cudaStreamWaitEvent(g, cm.ev_ready, 0));
   mark(0, g);

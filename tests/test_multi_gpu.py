@@ -35,3 +35,25 @@ def test_sharded_build_matvec_and_eigh_match_oracle(world, shard_build):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)  # a collective mismatch hangs: fail fast
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MP_WORKER_OK" in out.stdout
+
+
+@pytest.mark.parametrize("fail_rank", [None, 1])
+def test_copy_engine_exchange_and_its_fallback(fail_rank):
+    """SPED_EXCHANGE=ce: the shard exchange runs on the copy engines over IPC-mapped peer memory; when
+    one rank cannot set its side up (SPED_EXCHANGE_TEST_FAIL) every rank falls back to NCCL together."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, SPED_EXCHANGE="ce", SPED_LOG="1")
+    if fail_rank is not None:
+        env["SPED_EXCHANGE_TEST_FAIL"] = str(fail_rank)
+    names = ["heisenberg_square_4x4", "chain_8_k1_complex", "heisenberg_square_5x5"]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mp_worker.py")] + names
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MP_WORKER_OK" in out.stdout
+    log = out.stdout + out.stderr
+    if fail_rank is None:
+        assert "copy-engine exchange: two send buffers" in log
+    else:
+        assert "copy-engine exchange not available" in log
