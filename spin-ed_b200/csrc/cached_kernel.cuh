@@ -664,4 +664,53 @@ SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) code_
   }
 }
 
+// ---- placement after a staging traversal (several source classes) ---------------------------
+// The staging traversal (FillParams::stage) left, per lane, the elements of the row in traversal order --
+// position and code -- and the per-class counts in `len`.  With the class widths known from those
+// counts, this kernel lays them out exactly as the class-aware fill would: default-coefficient
+// elements from the front of their class region, coded ones from its back with the code in the compact
+// stream.  One canonicalisation per element instead of two (count + fill).
+struct PlaceParams {
+  RowDist dist;
+  u64 const* stage_off;   // [n_slices + 1] staging offsets (cheap width bound)
+  u32 const* stage_idx;
+  void const* stage_code;  // u8 / u16 per staging slot
+  CacheView out;           // slice_off, len, slice_start, n_classes, near, rounds, default_code, code_off of the final layout
+  u32* idx;                // final positions
+  void* code;              // final compact code stream
+};
+
+template <class Code>
+SPED_KERNEL_LINKAGE __global__ void __launch_bounds__(SPED_KERNEL_THREADS) cache_place_kernel(PlaceParams q) {
+  Code const* __restrict__ scode = static_cast<Code const*>(q.stage_code);
+  Code* __restrict__ ocode = static_cast<Code*>(q.code);
+  u64 const n_local = q.dist.n_local;
+  u32 const nc = q.out.n_classes;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (u64)gridDim.x * blockDim.x) {
+    u64 const slice = i >> 5, lane = i & 31;
+    u64 const sbase = __ldg(q.stage_off + slice) + lane;
+    u64 const fbase = __ldg(q.out.slice_off + slice) + lane;
+    u32 const width = (u32)((__ldg(q.out.slice_off + slice + 1) - __ldg(q.out.slice_off + slice)) >> 5);
+    u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u};
+    for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(q.out.slice_start + kClassStride * slice + (c - 1)) : width;
+    u32 total = 0;
+    for (u32 c = 0; c < nc; ++c)
+      total += (u32)__ldg(q.out.len + (u64)(2 * c) * n_local + i) + (u32)__ldg(q.out.len + (u64)(2 * c + 1) * n_local + i);
+    u32 cd[kMaxClasses] = {0u, 0u, 0u}, cx[kMaxClasses] = {0u, 0u, 0u};
+    for (u32 t = 0; t < total; ++t) {
+      u32 const pos = __ldg(q.stage_idx + sbase + (u64)t * 32);
+      u32 const code = (u32)scode[sbase + (u64)t * 32];
+      u32 const cls = dist_source_class(q.dist, pos, q.out.rounds, q.out.near);
+      if (code == q.out.default_code) {
+        q.idx[fbase + (u64)(start[cls] + cd[cls]) * 32] = pos;
+        ++cd[cls];
+      } else {
+        u32 const j = cx[cls]++;
+        q.idx[fbase + (u64)(start[cls + 1] - 1u - j) * 32] = pos;
+        ocode[__ldg(q.out.code_off + slice * nc + cls) + lane + (u64)j * 32] = (Code)code;
+      }
+    }
+  }
+}
+
 }  // namespace sped

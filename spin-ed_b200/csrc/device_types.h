@@ -166,6 +166,12 @@ struct FillParams {
   u64 row_lo, row_hi;      // local rows of this launch (multiples of 32, or the end): the fill runs in row
                            // chunks so that the code temporary stays small
   u64 code_slot0;          // first slot `code` covers = slice_off[row_lo / 32]
+  int stage;               // 1: staging traversal of a several-class build -- every element, whatever its
+                           // class, goes to the next slot of its lane (slice_off = staging offsets from the
+                           // cheap width bound) with its position in idx and its code in code (for ALL elements);
+                           // len gets the per-class counts.  cache_place_kernel then lays the elements out by
+                           // class without a second canonicalisation (cached_kernel.cuh).
+  int pad2_;
   u32 const* slice_start;  // several classes, fill pass: [n_slices][kClassStride] (see CacheView); null otherwise
   int count_only;          // exact class sizes wanted: first pass, only `len` is written
   u32 n_classes;

@@ -283,6 +283,84 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   stats[3] = n_classes;
   stats[4] = code_slots;
 
+  // ---- several classes: the one-traversal build (staging + cache_place_kernel) must produce the very
+  //      same arrays as the counting + filling traversals above ----
+  if (rounds > 0 && n_local) {
+    std::vector<u32> ub(n_slices, 0);
+    for (u64 s = 0; s < n_slices; ++s) {  // slice_width_kernel: cheap upper bound
+      u32 mx = 0;
+      for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i) {
+        u64 const r = pr.ix.reps[dist_local_to_global(d, i)];
+        u32 w = 0;
+        for (auto const& bd : pr.bonds) {
+          u32 a = 0;
+          for (u32 j = 0; j < bd.k; ++j) a |= (u32)((r >> ((bd.sites >> (8 * j)) & 0xffu)) & 1ull) << (bd.k - 1 - j);
+          w += (u32)__builtin_popcount((unsigned)pr.masks[bd.zoff + a]);
+        }
+        mx = std::max(mx, w);
+      }
+      ub[s] = mx;
+    }
+    std::vector<u64> stage_off(n_slices + 1, 0);
+    for (u64 s = 0; s < n_slices; ++s) stage_off[s + 1] = stage_off[s] + 32ull * ub[s];
+    std::vector<u32> stage_idx(std::max<u64>(stage_off[n_slices], 1), 0xabababab);
+    std::vector<unsigned char> stage_code(std::max<u64>(stage_off[n_slices], 1) * (wide ? 2 : 1), 0xcc);
+    std::vector<std::uint16_t> len2(len.size(), 0);
+    FillParams sp = fp;
+    sp.stage = 1;
+    sp.count_only = 0;
+    sp.slice_off = stage_off.data();
+    sp.slice_start = nullptr;
+    sp.idx = stage_idx.data();
+    sp.code = stage_code.data();
+    sp.code_slot0 = 0;
+    sp.len = len2.data();
+    sp.row_lo = 0;
+    sp.row_hi = n_local;
+    pr.with_canon([&](auto const& canon) { cache_fill_rows(sp, pr.terms, canon); });
+    if (overflow) fail(SPED_INTERNAL_ERROR, "emulated staging traversal: a row exceeded its slot bound");
+    if (len2 != len) fail(SPED_INTERNAL_ERROR, "emulation: staged and two-traversal class counts differ");
+    // class widths (class_width_kernel with split counts), offsets, compact code offsets
+    std::vector<u32> widths2(n_slices, 0), slice_start2(n_slices * kClassStride, 0), cw2(n_slices * n_classes, 0);
+    for (u64 s = 0; s < n_slices; ++s) {
+      u32 w[kMaxClasses] = {0, 0, 0};
+      for (u64 i = 32 * s; i < std::min<u64>(32 * s + 32, n_local); ++i)
+        for (u32 c = 0; c < n_classes; ++c)
+          w[c] = std::max<u32>(w[c], (u32)len2[(u64)(2 * c) * n_local + i] + (u32)len2[(u64)(2 * c + 1) * n_local + i]);
+      widths2[s] = w[0] + w[1] + w[2];
+      slice_start2[kClassStride * s] = w[0];
+      slice_start2[kClassStride * s + 1] = w[0] + w[1];
+    }
+    std::vector<u64> slice_off2(n_slices + 1, 0), code_off2(n_slices * n_classes + 1, 0);
+    for (u64 s = 0; s < n_slices; ++s) slice_off2[s + 1] = slice_off2[s] + 32ull * widths2[s];
+    code_width_kernel(len2.data(), n_local, n_classes, 0, n_slices, cw2.data());
+    for (u64 k = 0; k < n_slices * n_classes; ++k) code_off2[k + 1] = code_off2[k] + 32ull * cw2[k];
+    std::vector<u32> idx2(std::max<u64>(slice_off2[n_slices], 1), 0xdeadbeefu);
+    std::vector<unsigned char> compact2(std::max<u64>(code_off2[n_slices * n_classes], 1) * (wide ? 2 : 1), 0xdd);
+    PlaceParams q{};
+    q.dist = d;
+    q.stage_off = stage_off.data();
+    q.stage_idx = stage_idx.data();
+    q.stage_code = stage_code.data();
+    q.out.slice_off = slice_off2.data();
+    q.out.len = len2.data();
+    q.out.slice_start = slice_start2.data();
+    q.out.n_slices = n_slices;
+    q.out.n_classes = n_classes;
+    q.out.near = near;
+    q.out.rounds = rounds;
+    q.out.default_code = cm.default_code;
+    q.out.code_off = code_off2.data();
+    q.idx = idx2.data();
+    q.code = compact2.data();
+    if (wide) cache_place_kernel<std::uint16_t>(q);
+    else cache_place_kernel<std::uint8_t>(q);
+    if (slice_off2 != slice_off || slice_start2 != slice_start || code_off2 != code_off)
+      fail(SPED_INTERNAL_ERROR, "emulation: staged and two-traversal layouts differ");
+    if (idx2 != idx) fail(SPED_INTERNAL_ERROR, "emulation: staged and two-traversal positions differ");
+    if (compact2 != compact) fail(SPED_INTERNAL_ERROR, "emulation: staged and two-traversal code streams differ");
+  }
+
   // ---- streaming kernel: all classes in one pass, then class by class ----
   CachedParams cp{};
   cp.cache = CacheView{slice_off.data(), idx.data(), compact.data(), len.data(), n_classes > 1 ? slice_start.data() : nullptr,

@@ -234,10 +234,13 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
     u64 const slice = i >> 5;
     u64 base = 0;
     u32 start[kMaxClasses + 1] = {0u, 0u, 0u, 0u};  // first slot of each class; start[c >= n_classes] = width
+    bool const stage = p.stage != 0;
+    u32 width = 0, staged = 0;  // staging traversal: slots of the lane, elements written so far
     if (!count_only) {
       base = __ldg(p.slice_off + slice) + (i & 31);
-      u32 const width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
-      for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(p.slice_start + kClassStride * slice + (c - 1)) : width;
+      width = (u32)((__ldg(p.slice_off + slice + 1) - __ldg(p.slice_off + slice)) >> 5);
+      if (!stage)
+        for (u32 c = 1; c <= (u32)kMaxClasses; ++c) start[c] = c < nc ? __ldg(p.slice_start + kClassStride * slice + (c - 1)) : width;
     }
     // per class: cd = elements with the default coefficient (stored from the front of the class
     // region), cx = coded elements (stored from its back)
@@ -258,6 +261,18 @@ __device__ __forceinline__ void cache_fill_rows(FillParams const& p, TermsView c
       u32 const nd = cd[cls], nx = cx[cls];
       if (dflt) ++cd[cls]; else ++cx[cls];
       if (count_only) return;
+      if (stage) {  // traversal order, all classes together; the code of every element is kept
+        if (staged >= width) {
+          *p.overflow = 1;
+          return;
+        }
+        u64 const at = base + (u64)staged * 32;
+        ++staged;
+        p.idx[at] = (u32)pos;
+        if (p.code_wide) static_cast<dev_u16*>(p.code)[at - p.code_slot0] = (dev_u16)code;
+        else static_cast<dev_u8*>(p.code)[at - p.code_slot0] = (dev_u8)code;
+        return;
+      }
       u32 const lo = start[cls], hi = start[cls + 1];
       if (lo + nd + nx >= hi) {  // the two ends would meet
         *p.overflow = 1;

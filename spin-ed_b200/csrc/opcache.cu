@@ -55,14 +55,16 @@ __global__ void __launch_bounds__(kThreads) slice_width_kernel(RowContext ctx, T
 
 // Several classes: per slice class c takes max_lanes len_c slots per lane; widths[s] is their sum
 // and slice_start[s] = first slot of classes 1, 2, 3.
+// `split`: len holds (default, coded) counts per class (after a staging traversal) instead of class totals.
 __global__ void __launch_bounds__(kThreads) class_width_kernel(std::uint16_t const* len, u64 n_local, u32 n_classes,
-                                                               u32* widths, u32* slice_start) {
+                                                               u32* widths, u32* slice_start, bool split) {
   u64 const n_padded = (n_local + 31) & ~(u64)31;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (u64)gridDim.x * blockDim.x) {
     u32 w[kMaxClasses] = {0u, 0u, 0u};
 #pragma unroll
     for (u32 c = 0; c < (u32)kMaxClasses; ++c) {
       u32 v = (c < n_classes && i < n_local) ? len[(u64)(2 * c) * n_local + i] : 0u;  // count pass: class totals
+      if (split && c < n_classes && i < n_local) v += len[(u64)(2 * c + 1) * n_local + i];
       w[c] = __reduce_max_sync(0xffffffffu, v);
     }
     if ((i & 31) == 0) {
@@ -248,6 +250,13 @@ __global__ void __launch_bounds__(kThreads) sum_len_kernel(std::uint16_t const* 
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) mine += len[i];
   for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
+// SPED_FILL_STAGED=0: several-class caches are built with a counting and a filling traversal (the
+// fallback when the staging area does not fit) instead of one traversal plus a placement pass.
+bool staged_fill_enabled() {
+  char const* e = std::getenv("SPED_FILL_STAGED");
+  return !(e && e[0] == '0');
 }
 
 int env_cache_mode() {
@@ -480,12 +489,112 @@ bool Operator::cache_usable() {
   // slice widths: one class -- the cheap upper bound (transitions with a non-zero matrix element);
   // two classes -- exact per-class counts from a first traversal
   DeviceBuffer<u32> d_widths(c_slices);
+  // Several classes: ONE traversal into a staging area (every element in the next slot of its lane,
+  // slots from the cheap width bound), then a placement kernel that lays the elements out by class --
+  // when the staging area (4 + code bytes per slot) fits beside the cache; else count + fill traversals.
+  bool staged_done = false;
+  if (two && staged_fill_enabled()) {
+    DeviceBuffer<u32> d_ub(c_slices);
+    if (tsm > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(slice_width_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    slice_width_kernel<<<persistent_grid(n_local, kThreads, 8), kThreads, tsm>>>(mp.ctx, mp.terms, d_ub.ptr);
+    KERNEL_LAUNCHED();
+    DeviceBuffer<u64> d_stage_off(c_slices + 1);
+    slice_scan_kernel<<<1, 1024>>>(d_ub.ptr, d_stage_off.ptr, c_slices);
+    KERNEL_LAUNCHED();
+    CUDA_CHECK(cudaGetLastError());
+    u64 stage_slots = 0;
+    CUDA_CHECK(cudaMemcpy(&stage_slots, d_stage_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    // the final layout pads every class separately: allow for 1.35 x the staging slots
+    u64 const stage_bytes = stage_slots * (4 + code_bytes);
+    u64 const final_guess = (u64)(1.35 * (double)stage_slots) * 4 + n_local * 8 * c_classes;
+    if (stage_bytes + final_guess < free_b - free_b / 8) {
+      DeviceBuffer<u32> d_stage_idx(std::max<u64>(stage_slots, 1));
+      DeviceBuffer<unsigned char> d_stage_code(std::max<u64>(stage_slots, 1) * code_bytes);
+      fp.stage = 1;
+      fp.count_only = 0;
+      fp.slice_off = d_stage_off.ptr;
+      fp.slice_start = nullptr;
+      fp.idx = d_stage_idx.ptr;
+      fp.code = d_stage_code.ptr;
+      fp.code_slot0 = 0;
+      launch_fill();
+      fp.stage = 0;
+      CUDA_CHECK(cudaDeviceSynchronize());
+      int overflow = 0;
+      CUDA_CHECK(cudaMemcpy(&overflow, d_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+      if (overflow) return reject("internal: a row exceeded its staging slot bound");
+      // final layout from the per-class counts: class widths, offsets, compact code offsets
+      c_slice_start.alloc(c_slices * kClassStride);
+      class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, d_widths.ptr,
+                                                                                   c_slice_start.ptr, true);
+      KERNEL_LAUNCHED();
+      c_slice_off.alloc(c_slices + 1);
+      slice_scan_kernel<<<1, 1024>>>(d_widths.ptr, c_slice_off.ptr, c_slices);
+      KERNEL_LAUNCHED();
+      u64 const n_regions = c_slices * c_classes;
+      DeviceBuffer<u32> d_cw(std::max<u64>(n_regions, 1));
+      code_width_kernel<<<persistent_grid(c_slices, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, 0, c_slices, d_cw.ptr);
+      KERNEL_LAUNCHED();
+      c_code_off.alloc(n_regions + 1);
+      slice_scan_kernel<<<1, 1024>>>(d_cw.ptr, c_code_off.ptr, n_regions);
+      KERNEL_LAUNCHED();
+      CUDA_CHECK(cudaGetLastError());
+      u64 code_slots = 0;
+      CUDA_CHECK(cudaMemcpy(&c_slots, c_slice_off.ptr + c_slices, 8, cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(&code_slots, c_code_off.ptr + n_regions, 8, cudaMemcpyDeviceToHost));
+      u64 const need = c_slots * 4 + code_slots * code_bytes + n_local * 4 * c_classes + (c_slices + 1) * 16 + (n_regions + 1) * 8 + n_codes * 24;
+      CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+      u64 held = 0;
+      for (auto const& w : eigh_ws) held += w.count;
+      u64 const wanted = 4 * n_local * 16;
+      u64 const reserve = std::max<u64>((u64)2 << 30, wanted > held ? wanted - held : 0);
+      // (the staging area is released before the solver allocates anything: it does not count against the reserve)
+      if (mode != 1 && need + reserve > free_b + stage_bytes) return reject("does not fit in the free device memory (with room for the solver's vectors)");
+      if (c_slots * 4 + code_slots * code_bytes > free_b - free_b / 16) return reject("does not fit in device memory");
+      c_idx.alloc(std::max<u64>(c_slots, 1));
+      c_code.alloc(std::max<u64>(code_slots, 1) * code_bytes);
+      CUDA_CHECK(cudaMemsetAsync(c_code.ptr, 0, std::max<u64>(code_slots, 1) * code_bytes));
+      PlaceParams q{};
+      q.dist = dist;
+      q.stage_off = d_stage_off.ptr;
+      q.stage_idx = d_stage_idx.ptr;
+      q.stage_code = d_stage_code.ptr;
+      q.out.slice_off = c_slice_off.ptr;
+      q.out.len = c_len.ptr;
+      q.out.slice_start = c_slice_start.ptr;
+      q.out.n_slices = c_slices;
+      q.out.n_classes = c_classes;
+      q.out.near = c_near;
+      q.out.rounds = c_rounds;
+      q.out.default_code = c_default_code;
+      q.out.code_off = c_code_off.ptr;
+      q.idx = c_idx.ptr;
+      q.code = c_code.ptr;
+      int const grid = persistent_grid(n_local, kThreads, 8);
+      if (c_code_wide) cache_place_kernel<std::uint16_t><<<grid, kThreads>>>(q);
+      else cache_place_kernel<std::uint8_t><<<grid, kThreads>>>(q);
+      KERNEL_LAUNCHED();
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaDeviceSynchronize());
+      cache_bytes = need;
+      cache_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      cache_ready = true;
+      SPED_LOG("operator cache: %llu slots, %.2f GB, built in %.3f s (one traversal + placement)", (unsigned long long)c_slots,
+               need / 1e9, cache_build_seconds);
+      staged_done = true;
+    } else {
+      SPED_LOG("operator cache: no room for the staging area (%.1f GB): counting and filling in two traversals", stage_bytes / 1e9);
+    }
+  }
+  if (staged_done) return true;
   if (two) {
     fp.count_only = 1;
     launch_fill();
     c_slice_start.alloc(c_slices * kClassStride);
     class_width_kernel<<<persistent_grid(c_slices * 32, kThreads, 8), kThreads>>>(c_len.ptr, n_local, c_classes, d_widths.ptr,
-                                                                                 c_slice_start.ptr);
+                                                                                 c_slice_start.ptr, false);
     fp.count_only = 0;
     fp.slice_start = c_slice_start.ptr;
   } else {

@@ -57,3 +57,17 @@ def test_copy_engine_exchange_and_its_fallback(fail_rank):
         assert "copy-engine exchange: two send buffers" in log
     else:
         assert "copy-engine exchange not available" in log
+
+
+def test_two_traversal_cache_build_still_works():
+    """Several-class caches are built by one staging traversal plus a placement pass; the counting +
+    filling traversals remain as the fallback for when the staging area does not fit (SPED_FILL_STAGED=0)."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, SPED_FILL_STAGED="0", SPED_FILL_CHUNK_BYTES="400")
+    names = ["heisenberg_square_4x4", "chain_8_k1_complex", "heisenberg_square_5x5"]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "mp_worker.py")] + names
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MP_WORKER_OK" in out.stdout
