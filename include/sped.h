@@ -163,11 +163,13 @@ int sped_operator_matmat_device(void const* op, int dtype, uint64_t block_size, 
                                 uint64_t x_stride, void* y_local, uint64_t y_stride, void* stream);
 /* One column, row-sharded over the ranks of the communicator: x_local holds this rank's n_local
  * entries, x_replicated is a [world * chunk] DEVICE work vector in the [rank][local] layout (left
- * holding the gathered vector), y_local receives this rank's rows.  The NCCL all-gather of the
- * shards runs on the library's own stream and overlaps the part of the product whose source
- * entries this rank owns; only the remote-source part waits for it.  This is what sped_eigh does
- * per matvec; the per-row summation order (local class, then remote class) depends on the
- * number of ranks, so results agree across rank counts to rounding, not bitwise. */
+ * holding the gathered vector), y_local receives this rank's rows.  The exchange of the shards -- one
+ * NCCL all-gather, or for shards of 64 MB and more two rounds of copy-engine pulls from the peers'
+ * IPC-mapped send buffers (SPED_EXCHANGE=ce|nccl forces either) -- runs on the library's own streams
+ * and overlaps the part of the product whose source entries this rank owns; only the remote-source
+ * parts wait for it.  This is what sped_eigh does per matvec; the per-row summation order (local
+ * class, then the remote classes) depends on the number of ranks, so results agree across rank
+ * counts to rounding, not bitwise.  Collective: every rank of the communicator must call it. */
 int sped_operator_matvec_sharded(void const* op, int dtype, void const* x_local, void* y_local, void* x_replicated,
                                  void* stream);
 /* Host-pointer form of the row-sharded product, for a rank-parallel host eigensolver (PRIMME's
