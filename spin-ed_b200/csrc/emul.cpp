@@ -22,6 +22,7 @@
 #define __launch_bounds__(...)
 #endif
 #define SPED_KERNEL_LINKAGE static
+#define SPED_KERNEL_THREADS 32  // one emulated warp per block: block_reduce_store sums blockDim / 32 warp results
 namespace {
 struct Dim1 { unsigned x, y, z; };
 }
@@ -32,8 +33,13 @@ static inline void __syncwarp() {}
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
+// the other lanes of the emulated warp hold nothing: a shuffle from them contributes zero
+template <class T> static inline T __shfl_down_sync(unsigned, T, int) { return T(0); }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+
 #include "canon.cuh"          // ProgramCanon, TrivialCanon (+ matvec_kernel.cuh)
 #include "cached_kernel.cuh"  // the streaming kernel
+#include "eigh_kernels.cuh"   // fused kernels of the single-pair eigensolver iteration
 
 namespace sped {
 namespace {
@@ -453,5 +459,44 @@ extern "C" int sped_selftest_emulate_matvec(void const* op_handle, uint64_t n, u
     else
       run<double2>(pr, static_cast<double2 const*>(x_global), static_cast<double2*>(y_free), static_cast<double2*>(y_all),
                    static_cast<double2*>(y_phased), stats, ncols, static_cast<double2*>(y_block));
+  });
+}
+
+namespace sped {
+namespace {
+template <class T>
+void run_restart(uint64_t n, int m, int p, T* V, T* W, uint64_t ld, double2 const* C, double theta, double* out) {
+  std::vector<double2> partial(1 + (size_t)p + 1, make_double2(0, 0)), partial2(2, make_double2(0, 0));
+  if (m <= 4) restart_residual_kernel<T, 4>(V, W, ld, m, p, C, theta, n, partial.data());
+  else restart_residual_kernel<T, 8>(V, W, ld, m, p, C, theta, n, partial.data());
+  for (int j = 0; j < 1 + p; ++j) {  // finish_dot_kernel with one block: the partial is the sum
+    out[2 * j] = partial[j].x;
+    out[2 * j + 1] = partial[j].y;
+  }
+  T* w = V + (uint64_t)p * ld;
+  axpy_norm_kernel<T>(V, ld, p, partial.data() + 1, w, n, partial2.data());
+  out[2 * (1 + p)] = partial2[0].x;
+  double kept = 0;
+  int flag = 0;
+  scale_rel_kernel<T>(w, n, partial2.data(), partial.data(), 1e-24, &kept, &flag);
+  out[2 * (1 + p) + 1] = kept;
+  out[2 * (1 + p) + 2] = (double)flag;
+}
+}  // namespace
+}  // namespace sped
+
+extern "C" int sped_selftest_emulate_restart(int dtype, uint64_t n, int m, int p, void* V, void* W, uint64_t ld,
+                                             double const* C_re_im, double theta, double* out) {
+  return guard([&] {
+    if (m < 2 || m > 8 || p < 1 || p >= m) fail(LS_INVALID_ARGUMENT, "emulated restart: 2 <= m <= 8, 1 <= p < m");
+    std::vector<double2> C((size_t)m * p);
+    for (size_t i = 0; i < C.size(); ++i) C[i] = make_double2(C_re_im[2 * i], C_re_im[2 * i + 1]);
+    switch (dtype) {
+      case SPED_F32: run_restart<float>(n, m, p, static_cast<float*>(V), static_cast<float*>(W), ld, C.data(), theta, out); break;
+      case SPED_F64: run_restart<double>(n, m, p, static_cast<double*>(V), static_cast<double*>(W), ld, C.data(), theta, out); break;
+      case SPED_C64: run_restart<float2>(n, m, p, static_cast<float2*>(V), static_cast<float2*>(W), ld, C.data(), theta, out); break;
+      case SPED_C128: run_restart<double2>(n, m, p, static_cast<double2*>(V), static_cast<double2*>(W), ld, C.data(), theta, out); break;
+      default: fail(LS_INVALID_DATATYPE, "unknown datatype tag");
+    }
   });
 }

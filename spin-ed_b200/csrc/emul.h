@@ -18,6 +18,13 @@ extern "C" {
 int sped_selftest_emulate_matvec(void const* op, uint64_t n, uint64_t const* reps, uint16_t const* stab, int world, int rank,
                                  int dtype, void const* x_global, void* y_free, void* y_all, void* y_phased,
                                  uint64_t* stats, unsigned ncols, void* y_block);
+/* Host emulation of the fused kernels of the single-pair eigensolver iteration (csrc/eigh_kernels.cuh):
+ * restart_residual_kernel on V, W (n x m, column-major, leading dimension ld, in place; V needs m
+ * columns, column p receives the residual), then axpy_norm_kernel and scale_rel_kernel on that column.
+ * C: m x p complex, row-major, (re, im) pairs.  out: (re, im) of |r|^2 and of <V'_q, r> for q < p,
+ * then |t|^2, the kept share |t|^2 / |r|^2, and the DGKS flag. */
+int sped_selftest_emulate_restart(int dtype, uint64_t n, int m, int p, void* V, void* W, uint64_t ld,
+                                  double const* C_re_im, double theta, double* out);
 #ifdef __cplusplus
 }
 #endif

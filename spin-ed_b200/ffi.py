@@ -130,6 +130,7 @@ SIGNATURES = {
 EMUL_LIB_PATH = os.path.join(_HERE, "lib", "libsped_emul.so")
 EMUL_SIGNATURES = {
     "sped_selftest_emulate_matvec": (_ci, [_vp, _u64, _vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, C.c_uint, _vp]),
+    "sped_selftest_emulate_restart": (_ci, [_ci, _u64, _ci, _ci, _vp, _vp, _u64, _vp, C.c_double, _vp]),
 }
 _emul_lib = None
 

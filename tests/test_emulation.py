@@ -85,3 +85,59 @@ def test_emulated_kernels_match_oracle(oracle, name, groups, monkeypatch):
                 if len(rows):
                     err = np.linalg.norm(blk - wantb[rows])
                     assert err <= 1e-12 * np.linalg.norm(wantb), (name, ncols, world, rank, err)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.complex128, np.float32, np.complex64])
+@pytest.mark.parametrize("m,p", [(2, 1), (3, 2), (4, 2), (4, 3), (5, 2), (8, 7)])
+def test_emulated_fused_restart_residual_kernels(dt, m, p):
+    """eigh_kernels.cuh on the host: the fused restart + residual pass of the single-pair eigensolver
+    iteration, the axpy + norm pass and the relative scaling must equal the plain linear algebra they
+    stand for: V' = V C, W' = W C, r = (W - theta V) C[:, 0] in column p of V, |r|^2 and V'^H r, then
+    t = r - V' (V'^H r), |t|^2, t / |t|."""
+    rng = np.random.default_rng(1000 * m + 10 * p + np.dtype(dt).itemsize)
+    n = 777
+    cplx = np.dtype(dt).kind == "c"
+    wide = np.complex128 if cplx else np.float64
+
+    def rand(*shape):
+        a = rng.standard_normal(shape)
+        return a + 1j * rng.standard_normal(shape) if cplx else a
+
+    V = np.linalg.qr(rand(n, m))[0]
+    A = rand(n, n)
+    A = A + A.conj().T
+    W = A @ V
+    H = V.conj().T @ W
+    theta = float(np.linalg.eigvalsh(0.5 * (H + H.conj().T))[0])
+    C = np.linalg.qr(rand(m, p))[0].astype(np.complex128)
+    Vs = np.asfortranarray(V.astype(dt))
+    Ws = np.asfortranarray(W.astype(dt))
+    V0, W0 = Vs.astype(wide), Ws.astype(wide)  # what the kernel reads (storage precision)
+    Cw = C if cplx else C.real.astype(np.float64)
+    if not cplx:
+        C = C.real.astype(np.complex128)
+    c_pairs = np.ascontiguousarray(np.stack([C.real, C.imag], axis=-1).reshape(-1))
+    out = np.zeros(2 * (1 + p) + 3)
+    ffi.checkStatus(ffi.emulLib().sped_selftest_emulate_restart(
+        ffi.DTYPE_TAGS[np.dtype(dt)], n, m, p, Vs.ctypes.data, Ws.ctypes.data, n, c_pairs.ctypes.data, theta, out.ctypes.data))
+    store = lambda a: a.astype(dt).astype(wide)  # noqa: E731 -- rounding to the storage type
+    Vp, Wp = V0 @ Cw, W0 @ Cw
+    r = store((W0 - theta * V0) @ Cw[:, 0])
+    tol = 1e-12 if np.dtype(dt).itemsize >= 8 and np.dtype(dt) != np.complex64 else 2e-5
+    scale = np.linalg.norm(W0)
+    assert np.allclose(Ws[:, :p], Wp, rtol=0, atol=tol * scale)
+    assert np.allclose(Vs[:, :p], Vp, rtol=0, atol=tol)
+    sums = out[:2 * (1 + p)].reshape(1 + p, 2)
+    assert abs(sums[0, 0] - np.vdot(r, r).real) <= tol * max(1.0, np.vdot(r, r).real)
+    d = store(Vp).conj().T @ r
+    got_d = sums[1:, 0] + 1j * sums[1:, 1]
+    assert np.allclose(got_d, d, rtol=0, atol=tol * np.linalg.norm(r) + 1e-300)
+    t = store(r - store(Vp) @ got_d) if cplx else store(r - store(Vp).real @ got_d.real)
+    nt = np.vdot(t, t).real
+    assert abs(out[2 * (1 + p)] - nt) <= 10 * tol * max(nt, 1e-300)
+    assert abs(out[2 * (1 + p) + 1] - nt / np.vdot(r, r).real) <= 10 * tol
+    assert out[2 * (1 + p) + 2] == (1.0 if nt / np.vdot(r, r).real < 0.5 else 0.0)
+    assert np.allclose(Vs[:, p], t / np.sqrt(nt), rtol=0, atol=10 * tol)
+    # the restarted basis stays orthonormal and the new direction is orthogonal to it
+    G = Vs[:, :p + 1].astype(wide).conj().T @ Vs[:, :p + 1].astype(wide)
+    assert np.allclose(G, np.eye(p + 1), atol=50 * tol)
