@@ -21,6 +21,7 @@
 #include <mutex>
 #include <vector>
 #include <sstream>
+#include <thread>
 #include <tuple>
 
 #include "internal.h"
@@ -390,7 +391,9 @@ std::vector<char> read_cached_cubin(std::string const& path) {
 
 void write_cached_cubin(std::string const& path, std::vector<char> const& cubin) {
   // published atomically: several ranks may compile the same module at the same time
-  std::string tmp = path + "." + std::to_string((long)getpid()) + ".tmp";
+  // (process AND thread: two bases with the same program may be compiling in this process at once)
+  std::string tmp = path + "." + std::to_string((long)getpid()) + "." +
+                    std::to_string((unsigned long long)std::hash<std::thread::id>()(std::this_thread::get_id())) + ".tmp";
   FILE* f = std::fopen(tmp.c_str(), "wb");
   if (!f) return;
   u64 const size = cubin.size(), sum = fnv1a(cubin.data(), cubin.size());
