@@ -288,6 +288,7 @@ void run(Problem& pr, T const* x_global, T* y_free, T* y_all, T* y_phased, u64* 
   stats[2] = dflt;
   stats[3] = n_classes;
   stats[4] = code_slots;
+  stats[5] = wide ? 2 : 1;  // bytes per coefficient code
 
   // ---- several classes: the one-traversal build (staging + cache_place_kernel) must produce the very
   //      same arrays as the counting + filling traversals above ----

@@ -11,8 +11,8 @@ extern "C" {
  * and stabiliser sizes the caller supplies (the test-suite takes them from the oracle): y = H x for
  * the rows rank `rank` of `world` owns, computed by the matrix-free row routine (y_free), by the
  * streaming kernel over all source classes at once (y_all) and class by class (y_phased).
- * dtype: 1 = f64, 3 = c128; x in global row order.  stats[5] = slots, stored elements, elements
- * with the default coefficient, source classes, entries of the compact code stream.  With ncols = 2..4 the block kernel is run as well
+ * dtype: 1 = f64, 3 = c128; x in global row order.  stats[6] = slots, stored elements, elements
+ * with the default coefficient, source classes, entries of the compact code stream, bytes per code.  With ncols = 2..4 the block kernel is run as well
  * on the columns x_c[g] = x[(g + c) mod n] (y_block: n_local x ncols, column-major).
  * Verification only: nothing in the product calls it. */
 int sped_selftest_emulate_matvec(void const* op, uint64_t n, uint64_t const* reps, uint16_t const* stab, int world, int rank,

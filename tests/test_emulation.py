@@ -24,7 +24,7 @@ def _emulate(op, reps, stab, world, rank, x, ncols=1):
     dt = x.dtype
     outs = [np.full(max(n_local, 1), 7.0, dtype=dt) for _ in range(3)]
     block = np.full((max(n_local, 1), max(ncols, 1)), 7.0, dtype=dt, order="F")
-    stats = (C.c_uint64 * 5)()
+    stats = (C.c_uint64 * 6)()
     ffi.checkStatus(ffi.emulLib().sped_selftest_emulate_matvec(
         op._ptr, n, reps.ctypes.data, stab.ctypes.data, world, rank, ffi.DTYPE_TAGS[np.dtype(dt)], x.ctypes.data,
         outs[0].ctypes.data, outs[1].ctypes.data, outs[2].ctypes.data, stats, ncols, block.ctypes.data))
@@ -32,6 +32,50 @@ def _emulate(op, reps, stab, world, rank, x, ncols=1):
     if ncols > 1:
         return rows, [o[:n_local] for o in outs], [int(v) for v in stats], block[:n_local]
     return rows, [o[:n_local] for o in outs], [int(v) for v in stats]
+
+
+def _wide_code_config():
+    """20-site J1-J2-J3 chain, momentum sector 1 of the translations: 3 distinct off-diagonal values x 20
+    phases x 6 stabiliser sizes = 360 coefficient codes -- more than a byte holds, so the cache stores
+    u16 codes (no shipped deck does)."""
+    n = 20
+
+    def heis(j):
+        return [[j, 0, 0, 0], [0, -j, 2 * j, 0], [0, 2 * j, -j, 0], [0, 0, 0, j]]
+
+    return {"basis": {"number_spins": n, "hamming_weight": n // 2,
+                      "symmetries": [{"permutation": [(i + 1) % n for i in range(n)], "sector": 1}]},
+            "hamiltonian": {"name": "J1-J2-J3", "terms": [
+                {"matrix": heis(1.0), "sites": [[i, (i + 1) % n] for i in range(n)]},
+                {"matrix": heis(0.4), "sites": [[i, (i + 2) % n] for i in range(n)]},
+                {"matrix": heis(0.15), "sites": [[i, (i + 3) % n] for i in range(n)]}]},
+            "observables": []}
+
+
+def test_emulated_kernels_with_two_byte_codes(oracle, monkeypatch):
+    monkeypatch.setenv("SPED_REMOTE_GROUPS", "2")
+    cfg = _wide_code_config()
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    n = ob.number_states
+    reps = np.ascontiguousarray(ob.states, dtype=np.uint64)
+    stab = np.ascontiguousarray(np.rint(ob.norms ** 2 * ob.group_size), dtype=np.uint16)
+    op = product_problem(cfg).cHamiltonian.operatorObject
+    x = np.ascontiguousarray(splitmix_vector(n, 0x5EED0001, np.complex128))
+    want = oop.matmat(x)
+    scale = np.linalg.norm(want)
+    for world in (1, 4):
+        for rank in range(world):
+            rows, (free, allc, phased), stats = _emulate(op, reps, stab, world, rank, x)
+            assert stats[5] == 2, "this configuration is meant to need u16 codes"
+            assert stats[1] > stats[2] > 0  # coded and default elements both occur
+            for got in (free, allc, phased):
+                assert np.linalg.norm(got - want[rows]) <= 1e-12 * scale
+    xb = np.asfortranarray(np.stack([np.roll(x, -c) for c in range(3)], axis=1))
+    wantb = oop.matmat(xb)
+    rows, _, _, blk = _emulate(op, reps, stab, 1, 0, x, 3)
+    assert np.linalg.norm(blk - wantb[rows]) <= 1e-12 * np.linalg.norm(wantb)
 
 
 @pytest.mark.parametrize("groups", ["1", "2"])

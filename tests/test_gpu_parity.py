@@ -387,6 +387,37 @@ def test_cache_filled_by_either_kernel_is_the_same(monkeypatch):
     assert outs[0] == outs[1] == outs[2]
 
 
+def test_two_byte_coefficient_codes(oracle, monkeypatch):
+    """More than 256 distinct (value, phase, stabiliser) triples: the operator cache stores u16 codes.
+    No shipped deck needs them; a 20-site J1-J2-J3 chain in momentum sector 1 does (360 codes).  Cached
+    (one chunk and many chunks), matrix-free and oracle results must agree."""
+    from test_emulation import _wide_code_config
+
+    cfg = _wide_code_config()
+    ob, terms = oracle_problem(oracle, cfg)
+    ob.build()
+    oop = oracle.Operator(ob, terms)
+    n = ob.number_states
+    x = np.asfortranarray(np.stack([splitmix_vector(n, 31 + c, np.complex128) for c in range(3)], axis=1))
+    want = oop.matmat(x)
+    outs = []
+    for chunk in ("", "500"):
+        monkeypatch.setenv("SPED_FILL_CHUNK_BYTES", chunk)
+        uc = product_problem(cfg)
+        ffi.buildBasis(uc.cBasis)
+        assert np.array_equal(ffi.basisGetStates(uc.cBasis), ob.states)
+        op = uc.cHamiltonian.operatorObject
+        ffi.operatorSetCache(op, 0)
+        free = ffi.apply(op, x)
+        ffi.operatorSetCache(op, 1)
+        cached = ffi.apply(op, x)
+        assert ffi.operatorCacheInfo(op)["ready"]
+        for got in (free, cached):
+            assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+        outs.append(cached.tobytes())
+    assert outs[0] == outs[1]
+
+
 def test_jit_and_interpreted_kernels_agree_bitwise(monkeypatch):
     cfg = decks.load("heisenberg_square_5x5")
     n_expected = 208012
