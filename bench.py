@@ -14,6 +14,7 @@ buffers (H2D of x and D2H of y inside the timed region).  One JSON line on stdou
 from __future__ import annotations
 
 import argparse
+import re
 import json
 import os
 import statistics
@@ -656,6 +657,20 @@ def bench_deck(ctx, name, args, headline, solves="both"):
     if not args.no_parity and not huge:
         run_parity()
 
+    # Heisenberg rings: the eigenvalue against the EXACT Bethe-ansatz ground-state energy (oracle/bethe.py --
+    # shares no algorithm with the product; north_star asks for <= 1e-10 relative)
+    ring = re.fullmatch(r"heisenberg_chain_(\d+)", name)
+    if ring and extra.get("eigenvalues") and not args.no_parity:
+        from oracle import bethe
+
+        exact = bethe.sigma_sigma_ring_energy(int(ring.group(1)))
+        rel = abs(extra["eigenvalues"][0] - exact) / abs(exact)
+        extra["E0_bethe_ansatz"] = exact
+        extra["E0_rel_diff_vs_bethe_ansatz"] = rel
+        log(f"[rank {rank}] {name}: E0 {extra['eigenvalues'][0]:.12f} vs Bethe ansatz {exact:.12f}: relative difference {rel:.1e}")
+        if rel > 1e-10:
+            raise SystemExit(f"{name}: E0 {extra['eigenvalues'][0]!r} differs from the exact Bethe-ansatz value {exact!r} by {rel:.2e}")
+
     # CPU baseline (rank 0, one GPU only): the oracle port on the host cores, bounded row sample
     cpu_baseline = None
     if headline and rank == 0 and world == 1 and not args.no_cpu:
@@ -717,6 +732,7 @@ def run_ours(args):
             "roofline_frac_kernel": s["achieved"] / s["peak"],
             "roofline_frac_on_step": s["alg_bytes"] / (s["ms_per_step"] * 1e-3) / 1e9 / s["peak"],
             "E0": (sx.get("eigenvalues") or [None])[0], "rnorm": (sx.get("residual_norms") or [None])[0],
+            "E0_bethe_ansatz": sx.get("E0_bethe_ansatz"), "E0_rel_diff_vs_bethe_ansatz": sx.get("E0_rel_diff_vs_bethe_ansatz"),
             "matvecs": sx.get("eigh_matvecs"), "time_to_ground_state_s": sx.get("time_to_ground_state_s"),
             "time_to_ground_state_cold_s": sx.get("time_to_ground_state_cold_s"),
             "sample_parity_rel_l2": sx.get("sample_parity_rel_l2"), "basis_check": sx.get("basis_check"),

@@ -509,3 +509,18 @@ def test_ground_state_energy_agrees_between_sector_descriptions(n):
         e0.append(ev[0])
     assert dims[1] > 1.5 * dims[0]
     assert abs(e0[0] - e0[1]) <= 1e-10 * abs(e0[0]), (e0, dims)
+
+
+@pytest.mark.parametrize("n", [16, 20, 24])
+def test_ground_state_energy_equals_bethe_ansatz(n):
+    """The exact Bethe-ansatz energy of the Heisenberg ring (oracle/bethe.py: no basis, no symmetry
+    group, no sparse product, no eigensolver in common with the product) against sped_eigh in the fully
+    symmetric sector that holds the ground state for even n/2."""
+    from oracle import bethe
+
+    uc = product_problem(decks.chain(n, n // 2, 1, (0, 0)))
+    ffi.buildBasis(uc.cBasis)
+    ev, _, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 1)
+    exact = bethe.sigma_sigma_ring_energy(n)
+    assert abs(ev[0] - exact) <= 1e-10 * abs(exact), (n, ev[0], exact)
+    assert rn[0] <= 1e-8 * abs(exact)

@@ -162,3 +162,43 @@ def test_lazy_adoption_row_lists_and_window_enumeration(oracle, name):
         assert np.array_equal(inside, reps)
         pieces.append(reps)
     assert np.array_equal(np.concatenate(pieces), ob.states)
+
+
+def test_bethe_ansatz_exact_energies(oracle):
+    """oracle/bethe.py -- the exact Bethe-ansatz ground-state energy of the Heisenberg ring, an answer
+    that shares nothing with this repository's algorithms -- against the reference's known answers
+    (README 4-ring: -8, /root/reference/README.md:56-95; SURVEY 8c: chain_10 -18.061785418, chain_24
+    -42.6800580661), against dense diagonalisation of the oracle's matrices, and against the
+    eigenvalues the GPU path produced at full size (committed driver-command bench records)."""
+    import glob
+    import json
+    import os
+
+    from oracle import bethe
+
+    assert abs(bethe.sigma_sigma_ring_energy(4) + 8.0) < 1e-13
+    assert abs(bethe.sigma_sigma_ring_energy(10) + 18.061785418) < 1e-9
+    assert abs(bethe.sigma_sigma_ring_energy(24) + 42.6800580661) < 1e-9
+    for n in (6, 8, 12):  # unsymmetrised zero-magnetisation sector, dense
+        ob, terms = oracle_problem(oracle, decks.chain(n, n // 2))
+        ob.build()
+        e0 = np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())[0]
+        assert abs(e0 - bethe.sigma_sigma_ring_energy(n)) < 1e-12 * abs(e0)
+    # full size: what the B200 runs of this round measured (north_star: eigenvalues to <= 1e-10 relative)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = 0
+    for path in sorted(glob.glob(os.path.join(root, "profiles", "r02b_bench_*.json"))):
+        with open(path) as f:
+            d = json.load(f)
+        found = []
+        name = d["config"]["workload"]
+        if name.startswith("heisenberg_chain_") and d["extra"].get("eigenvalues"):
+            found.append((int(name.rsplit("_", 1)[1]), d["extra"]["eigenvalues"][0]))
+        c = d["extra"].get("chain_40")
+        if c and c.get("E0") is not None:
+            found.append((40, c["E0"]))
+        for n, e0 in found:
+            exact = bethe.sigma_sigma_ring_energy(n)
+            assert abs(e0 - exact) <= 1e-10 * abs(exact), (path, n, e0, exact)
+            seen += 1
+    assert seen >= 5  # chain_40 at 1/2/4/8 GPUs, chain_42 at 8, chain_24
