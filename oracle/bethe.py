@@ -1,4 +1,4 @@
-"""Exact ground-state energy of the spin-1/2 Heisenberg ring from the Bethe ansatz -- TEST INFRASTRUCTURE.
+"""Exact ground-state energies of spin-1/2 rings (Heisenberg: Bethe ansatz; XX: free fermions) -- TEST INFRASTRUCTURE.
 
 An answer that owes nothing to this repository's algorithms (no basis, no symmetry group, no sparse
 product, no eigensolver): for even N the ground state of H = J sum_i S_i.S_{i+1} is the Bethe state of
@@ -45,6 +45,20 @@ def ground_state_energy(n_sites: int, coupling: float = 1.0) -> float:
 def sigma_sigma_ring_energy(n_sites: int) -> float:
     """E0 of sum_i sigma_i.sigma_{i+1} (the matrix of the reference's Heisenberg decks) = 4 * E0(S.S)."""
     return 4.0 * ground_state_energy(n_sites)
+
+
+def xx_ring_energy(n_sites: int) -> float:
+    """Exact ground-state energy of sum_i (sx_i sx_{i+1} + sy_i sy_{i+1}) (Pauli matrices; two-site
+    matrix [[0,0,0,0],[0,0,2,0],[0,2,0,0],[0,0,0,0]]) on a ring of even n_sites at zero magnetisation:
+    free fermions after the Jordan-Wigner transformation, eps(k) = 4 cos k, momenta (2j+1) pi / n for
+    an even number of fermions (antiperiodic), 2 pi j / n for an odd one; the n/2 lowest levels filled.
+    A second exact answer, for a Hamiltonian with a different matrix (no diagonal part)."""
+    if n_sites < 4 or n_sites % 2:
+        raise ValueError("even number of sites >= 4")
+    m = n_sites // 2
+    j = np.arange(n_sites)
+    k = (2 * j + 1) * np.pi / n_sites if m % 2 == 0 else 2 * j * np.pi / n_sites
+    return float(np.sort(4.0 * np.cos(k))[:m].sum())
 
 
 if __name__ == "__main__":

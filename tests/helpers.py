@@ -61,6 +61,9 @@ def extra_configs():
     out["chain_40_hw3_k"] = decks.chain(40, 3, None, (20, 1))
     # spin inversion without a hamming-weight restriction
     out["chain_10_inv_nohw"] = decks.chain(10, None, 1, (0, 0))
+    # XX ring: a two-site matrix without a diagonal part (exact answer: free fermions, oracle/bethe.py)
+    out["xx_chain_12_sym"] = decks.chain(12, 6, 1, (0, 0))
+    out["xx_chain_12_sym"]["hamiltonian"]["terms"][0]["matrix"] = [[0, 0, 0, 0], [0, 0, 2, 0], [0, 2, 0, 0], [0, 0, 0, 0]]
     # 3-site and 1-site terms with a complex matrix: chirality-like term + field
     sx = np.array([[0, 1], [1, 0]], dtype=complex); sy = np.array([[0, -1j], [1j, 0]]); sz = np.diag([1.0 + 0j, -1.0])
     def kron3(a, b, c): return np.kron(a, np.kron(b, c))

@@ -14,7 +14,7 @@ from helpers import SMALL_DECKS, extra_configs, oracle_problem, product_problem,
 from spin_ed_b200 import decks, ffi
 
 NAMES = SMALL_DECKS + ["chain_12_full_sym", "chain_12_pi", "chain_8_k1_complex", "chain_9_k2_nohw", "chain_10_inv_only",
-                       "chain_10_inv_nohw", "chain_8_chiral_3site", "ring_4site_nosym", "chain_40_hw3_k"]
+                       "chain_10_inv_nohw", "chain_8_chiral_3site", "ring_4site_nosym", "chain_40_hw3_k", "xx_chain_12_sym"]
 
 
 def _emulate(op, reps, stab, world, rank, x, ncols=1):

@@ -524,3 +524,18 @@ def test_ground_state_energy_equals_bethe_ansatz(n):
     exact = bethe.sigma_sigma_ring_energy(n)
     assert abs(ev[0] - exact) <= 1e-10 * abs(exact), (n, ev[0], exact)
     assert rn[0] <= 1e-8 * abs(exact)
+
+
+@pytest.mark.parametrize("n", [16, 20])
+def test_xx_ring_ground_state_equals_free_fermions(n):
+    """XX ring (two-site matrix without a diagonal part): sped_eigh in the symmetric sector against the
+    exact free-fermion energy (oracle/bethe.py)."""
+    from oracle import bethe
+    from test_oracle import xx_chain
+
+    uc = product_problem(xx_chain(n, 1, (0, 0)))
+    ffi.buildBasis(uc.cBasis)
+    ev, _, rn = ffi.eigh(uc.cHamiltonian.operatorObject, np.float64, 1)
+    exact = bethe.xx_ring_energy(n)
+    assert abs(ev[0] - exact) <= 1e-10 * abs(exact), (n, ev[0], exact)
+    assert rn[0] <= 1e-8 * abs(exact)

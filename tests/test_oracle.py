@@ -202,3 +202,26 @@ def test_bethe_ansatz_exact_energies(oracle):
             assert abs(e0 - exact) <= 1e-10 * abs(exact), (path, n, e0, exact)
             seen += 1
     assert seen >= 5  # chain_40 at 1/2/4/8 GPUs, chain_42 at 8, chain_24
+
+
+XX_MATRIX = [[0, 0, 0, 0], [0, 0, 2, 0], [0, 2, 0, 0], [0, 0, 0, 0]]  # sx sx + sy sy
+
+
+def xx_chain(n, spin_inversion=None, sectors=None):
+    cfg = decks.chain(n, n // 2, spin_inversion, sectors)
+    cfg["hamiltonian"]["terms"][0]["matrix"] = XX_MATRIX
+    return cfg
+
+
+def test_xx_ring_free_fermion_energies(oracle):
+    """A second exact answer with a different two-site matrix (no diagonal part): the XX ring is free
+    fermions.  The oracle reproduces it without symmetries and in the symmetric sector that holds the
+    ground state (momentum 0 / parity + / inversion + for even n/2, momentum pi / - / - for odd n/2)."""
+    from oracle import bethe
+
+    for cfg, n in [(xx_chain(8), 8), (xx_chain(10), 10), (xx_chain(12), 12), (xx_chain(12, 1, (0, 0)), 12),
+                   (xx_chain(16, 1, (0, 0)), 16), (xx_chain(10, -1, (5, 1)), 10), (xx_chain(14, -1, (7, 1)), 14)]:
+        ob, terms = oracle_problem(oracle, cfg)
+        ob.build()
+        e0 = np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())[0]
+        assert abs(e0 - bethe.xx_ring_energy(n)) < 1e-12 * abs(e0), (n, e0)
