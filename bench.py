@@ -781,7 +781,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_DECK)
     ap.add_argument("--sharded-deck", default="heisenberg_chain_40",
-                    help="with more than one GPU this deck is measured as well (extra.<deck>); '' to skip")
+                    help="this deck is measured as well (extra.<deck>; on one GPU with a single solve); '' to skip")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--parity-rows", type=int, default=100_000, help="rows of the oracle parity sample")
     ap.add_argument("--e2e-host-gb", type=float, default=24.0, help="skip the host-buffer leg above this much pinned memory")

@@ -225,3 +225,24 @@ def test_xx_ring_free_fermion_energies(oracle):
         ob.build()
         e0 = np.linalg.eigvalsh(oracle.Operator(ob, terms).to_dense())[0]
         assert abs(e0 - bethe.xx_ring_energy(n)) < 1e-12 * abs(e0), (n, e0)
+
+
+def test_element_counts_of_unsymmetrised_decks_have_closed_forms(oracle):
+    """Without symmetries the number of off-diagonal elements is plain combinatorics: every bond
+    contributes once for each state in which its two spins are antiparallel.  chain_24 (hamming weight
+    12): 24 * 2 * C(22, 11); xxz_triangular_19 (no hamming-weight restriction, 57 bonds): 57 * 2^18.
+    The oracle's count and the count the GPU path reported at full size (committed bench records) must
+    both equal them."""
+    import json
+    import math
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, rows, elements in (("heisenberg_chain_24", math.comb(24, 12), 24 * 2 * math.comb(22, 11)),
+                                 ("xxz_triangular_19", 2 ** 19, 57 * 2 ** 18)):
+        with open(os.path.join(root, "profiles", f"r02b_bench_{name}_n1.json")) as f:
+            d = json.load(f)
+        assert d["config"]["rows"] == rows and d["config"]["offdiag_elements"] == elements, name
+    ob, terms = oracle_problem(oracle, decks.load("xxz_triangular_19"))
+    ob.build()
+    assert oracle.Operator(ob, terms).count_offdiag() == 57 * 2 ** 18
